@@ -1,0 +1,164 @@
+/*
+ * toyni_ntt_cuda.h — C ABI of the B200-native (sm_100a) BabyBear prover hot path.
+ *
+ * The library is a drop-in for the static library `ntt_cuda` that the reference links
+ * (`#[link(name = "ntt_cuda", kind = "static")]`, src/ntt.rs:95; built by build.rs:75-116 from
+ * cuda/ntt_kernel.cu).  Section 1 keeps, symbol for symbol, what src/ntt.rs:96-110 imports.
+ * Section 2 adds device-resident, stream-ordered entry points for the rest of the path
+ * (coset LDE, FRI fold, Merkle commit, FRI commit loop); section 3 the host-pointer forms
+ * that the reference call sites in src/math/domain.rs, src/math/fri.rs and src/fibonacci.rs
+ * would bind (see INTEGRATION.md for the Rust side).
+ *
+ * Conventions
+ *   - Host field arrays use the reference's storage: one canonical value in [0,p) per uint64_t
+ *     (`#[repr(C)] struct BabyBear { value: u64 }`, src/babybear.rs:10-14); an Ext is four of
+ *     them, limb order [a0,a1,a2,a3] (src/ext.rs:22-26).  p = 2013265921.
+ *   - Device field arrays are uint32_t (4 bytes per base element, 16 per Ext, same limb order).
+ *   - All `bb_*` functions return 0 on success or a cudaError_t value (also kept as a sticky
+ *     last error, bb_last_error()).  The void functions of section 1 record errors the same way.
+ *   - There is no CPU fallback: without a usable sm_100 device every compute entry point fails.
+ */
+#ifndef TOYNI_NTT_CUDA_H
+#define TOYNI_NTT_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * 1. Symbols the reference's Rust side already imports (src/ntt.rs:96-110).
+ *    `count` is in uint64_t elements (cuda/ntt_kernel.cu:298-312).
+ * ---------------------------------------------------------------------------------------- */
+int cuda_copy_to_device(uint64_t* d_dest, const uint64_t* h_src, size_t count);   /* src/ntt.rs:97  */
+int cuda_copy_from_device(uint64_t* h_dest, const uint64_t* d_src, size_t count); /* src/ntt.rs:98  */
+int cuda_malloc(uint64_t** d_ptr, size_t count);                                  /* src/ntt.rs:99  */
+int cuda_free(uint64_t* d_ptr);                                                   /* src/ntt.rs:100 */
+const char* cuda_get_error_string(int error);                                     /* src/ntt.rs:101 */
+/* cudaGetDeviceCount (src/ntt.rs:102) is resolved from libcudart, as in the reference. */
+
+/* Per-size context (src/ntt.rs:107; cuda/ntt_kernel.cu:213-234).  n must be a power of two with
+ * log2(n) <= 27, otherwise NULL (cuda/ntt_kernel.cu:220).  Contexts share one per-device twiddle
+ * cache generated on the device; a context owns its staging buffers and a stream and serialises
+ * concurrent callers itself. */
+void* ntt_ctx_create(uint32_t n);
+void ntt_ctx_destroy(void* ctx);                                                  /* cuda/ntt_kernel.cu:236 */
+/* Forward / inverse NTT, in place on HOST data, natural order in and out, canonical outputs
+ * (src/ntt.rs:108-109; cuda/ntt_kernel.cu:249-292).  Bit-exact with ntt()/intt() of
+ * src/ntt.rs:24-66 for the canonical root BabyBear::get_root_of_unity(log2 n). */
+void ntt_run_inplace(void* ctx, uint64_t* h_data);
+void intt_run_inplace(void* ctx, uint64_t* h_data);
+
+/* ------------------------------------------------------------------------------------------
+ * 2. Device-resident, stream-ordered API.
+ * ---------------------------------------------------------------------------------------- */
+int bb_last_error(void);                 /* sticky: first error since the last bb_clear_error() */
+const char* bb_last_error_string(void);
+void bb_clear_error(void);
+int bb_device_ok(void);                  /* 1 iff the current device is compute capability 10.x */
+/* Stream used by every later call on this host thread's library state (NULL = legacy default stream). */
+void bb_set_stream(void* cuda_stream);
+int bb_sync(void);                       /* synchronise that stream */
+
+int bb_dev_alloc(void** d_ptr, size_t bytes);
+int bb_dev_free(void* d_ptr);
+int bb_h2d(void* d_dst, const void* h_src, size_t bytes);            /* async on the stream */
+int bb_d2h(void* h_dst, const void* d_src, size_t bytes);            /* async on the stream */
+/* width conversion between the reference's u64 storage and device u32 (values are reduced mod p) */
+int bb_narrow_u64_to_u32(const uint64_t* d_src, uint32_t* d_dst, size_t count);
+int bb_widen_u32_to_u64(const uint32_t* d_src, uint64_t* d_dst, size_t count);
+
+/* dir: 0 forward (src/ntt.rs:24-53), 1 inverse incl. the n^-1 scale (src/ntt.rs:56-66). In place. */
+int bb_ntt_device(uint32_t* d_data, uint32_t log_n, int dir);
+/* `batch` independent vectors of 2^log_n elements, vector b at d_data + b * 2^log_n. */
+int bb_ntt_batch_device(uint32_t* d_data, uint32_t log_n, size_t batch, int dir);
+/* AoS extension-field array (4 limbs per element): the four coordinate transforms of
+ * transform_ext (src/math/domain.rs:140-151) in one go. */
+int bb_ntt_ext_device(uint32_t* d_data, uint32_t log_n, int dir);
+
+/* BabyBearDomain::fft on a coset (src/math/domain.rs:107-123,154-162): zero-pad/truncate the
+ * n_coeffs coefficients to 2^log_size, multiply by shift^i, forward NTT.  Fused into the first
+ * NTT pass: only the n_coeffs inputs are read.  shift == 1 is the plain domain.  d_out must not
+ * alias d_coeffs unless n_coeffs == 2^log_size.  limbs: 1 or 4 (fft_ext, :135-137). */
+int bb_coset_fft_device(const uint32_t* d_coeffs, size_t n_coeffs, uint32_t log_size, uint32_t shift, int limbs,
+                        uint32_t* d_out);
+/* BabyBearDomain::ifft (src/math/domain.rs:85-102,165-174): INTT then multiply by shift^-i
+ * (fused into the last pass together with n^-1).  In place.  limbs: 1 or 4 (ifft_ext, :130-132). */
+int bb_coset_ifft_device(uint32_t* d_evals, uint32_t log_size, uint32_t shift, int limbs);
+
+/* fri_fold / fri_fold_ext (src/math/fri.rs:27-48, :7-25) for evaluation points x_i = x0 * w_m^i,
+ * w_m = get_root_of_unity(log2 m): the layout the prover uses (src/fibonacci.rs:214,228-231 gives
+ * x0 = shift^(2^k) for layer k).  m values in, m/2 out; x^-1 is generated on chip.
+ * limbs: 1 (beta[0] used) or 4. */
+int bb_fri_fold_device(const uint32_t* d_evals, size_t m, uint32_t x0, const uint32_t beta[4], int limbs,
+                       uint32_t* d_out);
+/* Same for one shard of a cyclic multi-GPU layout: the shard holds global indices
+ * rank, rank+nranks, ...; m_local = m/nranks values in, m_local/2 out, no communication. */
+int bb_fri_fold_shard_device(const uint32_t* d_evals, size_t m_local, uint32_t log_m, uint32_t x0,
+                             const uint32_t beta[4], int limbs, uint32_t nranks, uint32_t rank, uint32_t* d_out);
+/* Reference signature with an explicit xs array (only xs[0..m/2) is read, src/math/fri.rs:13-16). */
+int bb_fri_fold_xs_device(const uint32_t* d_evals, size_t m, const uint32_t* d_xs, const uint32_t beta[4], int limbs,
+                          uint32_t* d_out);
+
+/* Merkle commitment (src/merkle.rs:16-48 with the prover's leaf encoding, src/fibonacci.rs:340-363):
+ * leaf i = SHA256(0x00 || salt_i[16] || LE-u64 of each limb), or without the salt when d_salts is
+ * NULL (build_unsalted_tree).  d_nodes receives every level, leaf level first, 32 bytes per node:
+ * bb_merkle_node_count(n) * 32 bytes.  root_out (host, 32 bytes) may be NULL; if given the call
+ * synchronises the stream. */
+size_t bb_merkle_node_count(size_t nleaves);
+int bb_merkle_commit_device(const uint32_t* d_vals, int limbs, size_t n, const uint8_t* d_salts, uint8_t* d_nodes,
+                            uint8_t* root_out);
+/* MerkleTree::new over arbitrary equal-length byte-string leaves already on the device. */
+int bb_merkle_build_bytes_device(const uint8_t* d_leaves, size_t n, size_t leaf_len, uint8_t* d_nodes, uint8_t* root_out);
+/* MerkleTree::get_proof (src/merkle.rs:50-80): path_out = depth*32 bytes (host), pos_out = depth flags. */
+int bb_merkle_open_device(const uint8_t* d_nodes, size_t nleaves, size_t index, uint8_t* path_out, uint8_t* pos_out,
+                          size_t* depth_out);
+
+/* The prover's FRI commit loop (src/fibonacci.rs:200-247) on device-resident data.
+ *   d_layer0   : n values (limbs u32 each) on the coset {shift * w_n^i}
+ *   final_size : stop when the layer has this many values (src/fibonacci.rs:220-222)
+ *   d_salts    : 16 bytes per leaf for every salted layer, layers back to back, layer 0 first
+ *                (the final layer is committed unsalted, :234-238)
+ *   challenge  : called once per fold with the root just committed (absorb) and must return
+ *                beta (squeeze) — limbs values; it is the host transcript (src/transcript.rs).
+ *                When NULL, betas_in supplies limbs values per fold (fold-only benchmarking).
+ *   d_layers   : receives all layers back to back (n + n/2 + ... + final_size values)
+ *   d_nodes    : receives the trees back to back (bb_merkle_node_count per layer); NULL skips hashing
+ *   roots_out  : 32 bytes per layer (host); NULL if d_nodes is NULL
+ * Returns the number of folds through *folds_out. */
+typedef void (*bb_challenge_fn)(void* user, const uint8_t root[32], uint32_t layer, uint32_t* beta_out);
+int bb_fri_commit_device(const uint32_t* d_layer0, size_t n, uint32_t shift, size_t final_size, int limbs,
+                         const uint8_t* d_salts, bb_challenge_fn challenge, void* user, const uint32_t* betas_in,
+                         uint32_t* d_layers, uint8_t* d_nodes, uint8_t* roots_out, size_t* folds_out);
+
+/* Tuning / introspection */
+int bb_ntt_set_plan(uint32_t log_n, int npass, const int* log_rows, const int* log_cols); /* npass 0 = default */
+int bb_ntt_get_plan(uint32_t log_n, int* log_rows, int* log_cols);                        /* returns npass */
+int bb_ntt_launches(uint32_t log_n);                    /* kernels launched per device-resident transform */
+unsigned long long bb_kernel_launch_count(void);        /* total launches of this library's kernels so far */
+int bb_warmup(uint32_t log_n);                          /* build tables and scratch for this size */
+void bb_release(void);                                  /* free all cached device memory on this device */
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Host-pointer forms of the reference call sites (u64 storage in and out).
+ *    Each does H2D + kernels + D2H on the library stream and returns after synchronising.
+ * ---------------------------------------------------------------------------------------- */
+/* BabyBearDomain::fft / ifft (src/math/domain.rs:107-123, :85-102) */
+int toyni_domain_fft(const uint64_t* coeffs, size_t n_coeffs, size_t size, uint64_t shift, uint64_t* evals_out);
+int toyni_domain_ifft(const uint64_t* evals, size_t size, uint64_t shift, uint64_t* coeffs_out);
+/* fft_ext / ifft_ext (src/math/domain.rs:129-137): AoS Ext arrays, 4 x u64 per element */
+int toyni_domain_fft_ext(const uint64_t* coeffs, size_t n_coeffs, size_t size, uint64_t shift, uint64_t* evals_out);
+int toyni_domain_ifft_ext(const uint64_t* evals, size_t size, uint64_t shift, uint64_t* coeffs_out);
+/* fri_fold / fri_fold_ext (src/math/fri.rs:27, :7): xs has at least m/2 entries */
+int toyni_fri_fold(const uint64_t* evals, size_t m, const uint64_t* xs, uint64_t beta, uint64_t* out);
+int toyni_fri_fold_ext(const uint64_t* evals, size_t m, const uint64_t* xs, const uint64_t beta[4], uint64_t* out);
+/* build_merkle_tree / build_unsalted_tree (src/fibonacci.rs:340-363): salts NULL = unsalted.
+ * nodes_out (host, bb_merkle_node_count(n)*32 bytes) may be NULL when only the root is wanted. */
+int toyni_merkle_commit(const uint64_t* values, size_t n, int limbs, const uint8_t* salts, uint8_t* nodes_out,
+                        uint8_t root_out[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,511 @@
+// C ABI of the library (include/toyni_ntt_cuda.h).  Section numbers follow the header.
+#include "../../include/toyni_ntt_cuda.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "fri_fold.cuh"
+#include "merkle.cuh"
+#include "ntt_engine.cuh"
+
+using namespace bb;
+
+// ------------------------------------------------------------------ library state
+static std::atomic<int> g_last_error{0};
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<cudaStream_t> g_stream{nullptr};
+
+static inline int note(int rc) {
+    if (rc != 0) {
+        int expected = 0;
+        g_last_error.compare_exchange_strong(expected, rc);
+    }
+    return rc;
+}
+#define CK(x)                                  \
+    do {                                       \
+        int rc_ = (int)(x);                    \
+        if (rc_ != 0) return note(rc_);        \
+    } while (0)
+
+static inline cudaStream_t cur_stream() { return g_stream.load(); }
+static inline bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
+static inline uint32_t log2_of(size_t v) {
+    uint32_t l = 0;
+    while (((size_t)1 << l) < v) l++;
+    return l;
+}
+
+// ------------------------------------------------------------------ width conversion kernels
+__global__ void __launch_bounds__(256) narrow_kernel(const uint64_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        uint64_t v = src[i];
+        // canonical inputs take the fast path; anything else is reduced like BabyBear::new (src/babybear.rs:26-30)
+        dst[i] = (v < (uint64_t)P) ? (uint32_t)v : (uint32_t)(v % (uint64_t)P);
+    }
+}
+__global__ void __launch_bounds__(256) widen_kernel(const uint32_t* __restrict__ src, uint64_t* __restrict__ dst, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = (uint64_t)src[i];
+}
+static inline unsigned conv_blocks(size_t n) {
+    size_t b = (n + 255) / 256;
+    return (unsigned)(b > 148 * 16 ? 148 * 16 : (b ? b : 1));
+}
+
+extern "C" {
+
+// ================================================================== 1. reference symbols
+int cuda_malloc(uint64_t** d_ptr, size_t count) { return note((int)cudaMalloc((void**)d_ptr, count * sizeof(uint64_t))); }
+int cuda_free(uint64_t* d_ptr) { return note((int)cudaFree(d_ptr)); }
+int cuda_copy_to_device(uint64_t* d_dest, const uint64_t* h_src, size_t count) {
+    return note((int)cudaMemcpy(d_dest, h_src, count * sizeof(uint64_t), cudaMemcpyHostToDevice));
+}
+int cuda_copy_from_device(uint64_t* h_dest, const uint64_t* d_src, size_t count) {
+    return note((int)cudaMemcpy(h_dest, d_src, count * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+}
+const char* cuda_get_error_string(int error) { return cudaGetErrorString((cudaError_t)error); }
+
+struct NttCtx {
+    uint32_t n, log_n;
+    uint64_t* d64;  // staging in the reference's width
+    uint32_t* d32;  // compute buffer
+    cudaStream_t stream;
+    std::mutex mu;  // the reference's context is not re-entrant (cuda/ntt_kernel.cu:246-248); this one serialises
+};
+
+void* ntt_ctx_create(uint32_t n) {
+    if (!is_pow2(n)) {
+        note((int)cudaErrorInvalidValue);
+        return nullptr;
+    }
+    uint32_t log_n = log2_of(n);
+    if (log_n > (uint32_t)MAX_LOG_N) return nullptr;  // cuda/ntt_kernel.cu:220
+    if (!bb_device_ok()) {
+        note((int)cudaErrorNoKernelImageForDevice);
+        return nullptr;
+    }
+    NttCtx* c = new NttCtx();
+    c->n = n;
+    c->log_n = log_n;
+    c->d64 = nullptr;
+    c->d32 = nullptr;
+    c->stream = nullptr;
+    if (note((int)cudaMalloc(&c->d64, (size_t)n * 8)) || note((int)cudaMalloc(&c->d32, (size_t)n * 4)) ||
+        note((int)cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) || note(engine_warmup((int)log_n))) {
+        ntt_ctx_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+void ntt_ctx_destroy(void* ctx) {
+    NttCtx* c = (NttCtx*)ctx;
+    if (!c) return;
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    cudaFree(c->d64);
+    cudaFree(c->d32);
+    delete c;
+}
+
+static void run_host_inplace(NttCtx* c, uint64_t* h, bool inverse) {
+    if (!c || !h) {
+        note((int)cudaErrorInvalidValue);
+        return;
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t n = c->n;
+    cudaStream_t s = c->stream;
+    if (note((int)cudaMemcpyAsync(c->d64, h, n * 8, cudaMemcpyHostToDevice, s))) return;
+    narrow_kernel<<<conv_blocks(n), 256, 0, s>>>(c->d64, c->d32, n);
+    NttDesc d{};
+    d.log_n = (int)c->log_n;
+    d.inverse = inverse;
+    d.in = c->d32;
+    d.out = c->d32;
+    d.n_in = n;
+    d.batch = 1;
+    d.batch_stride_in = d.batch_stride_out = n;
+    if (note(ntt_execute(d, s))) return;
+    widen_kernel<<<conv_blocks(n), 256, 0, s>>>(c->d32, c->d64, n);
+    g_launches += 2 + (unsigned)ntt_plan_for((int)c->log_n, 0, 1).npass;
+    if (note((int)cudaMemcpyAsync(h, c->d64, n * 8, cudaMemcpyDeviceToHost, s))) return;
+    note((int)cudaStreamSynchronize(s));
+}
+
+void ntt_run_inplace(void* ctx, uint64_t* h_data) { run_host_inplace((NttCtx*)ctx, h_data, false); }
+void intt_run_inplace(void* ctx, uint64_t* h_data) { run_host_inplace((NttCtx*)ctx, h_data, true); }
+
+// ================================================================== 2. device-resident API
+int bb_last_error(void) { return g_last_error.load(); }
+const char* bb_last_error_string(void) { return cudaGetErrorString((cudaError_t)g_last_error.load()); }
+void bb_clear_error(void) {
+    g_last_error.store(0);
+    cudaGetLastError();
+}
+int bb_device_ok(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10;
+}
+void bb_set_stream(void* cuda_stream) { g_stream.store((cudaStream_t)cuda_stream); }
+int bb_sync(void) { return note((int)cudaStreamSynchronize(cur_stream())); }
+
+int bb_dev_alloc(void** d_ptr, size_t bytes) { return note((int)cudaMalloc(d_ptr, bytes)); }
+int bb_dev_free(void* d_ptr) { return note((int)cudaFree(d_ptr)); }
+int bb_h2d(void* d_dst, const void* h_src, size_t bytes) {
+    return note((int)cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, cur_stream()));
+}
+int bb_d2h(void* h_dst, const void* d_src, size_t bytes) {
+    return note((int)cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, cur_stream()));
+}
+int bb_narrow_u64_to_u32(const uint64_t* d_src, uint32_t* d_dst, size_t count) {
+    if (count == 0) return 0;
+    narrow_kernel<<<conv_blocks(count), 256, 0, cur_stream()>>>(d_src, d_dst, count);
+    g_launches++;
+    return note((int)cudaGetLastError());
+}
+int bb_widen_u32_to_u64(const uint32_t* d_src, uint64_t* d_dst, size_t count) {
+    if (count == 0) return 0;
+    widen_kernel<<<conv_blocks(count), 256, 0, cur_stream()>>>(d_src, d_dst, count);
+    g_launches++;
+    return note((int)cudaGetLastError());
+}
+
+static int run_ntt(const uint32_t* in, uint32_t* out, uint32_t log_n, int log_inner, size_t n_in, size_t batch, int dir,
+                   uint32_t shift) {
+    if (log_n > (uint32_t)MAX_LOG_N || (dir != 0 && dir != 1)) return note((int)cudaErrorInvalidValue);
+    if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
+    NttDesc d{};
+    d.log_n = (int)log_n;
+    d.log_inner = log_inner;
+    d.inverse = dir == 1;
+    d.in = in;
+    d.out = out;
+    d.n_in = n_in;
+    d.batch = batch;
+    d.batch_stride_in = d.batch_stride_out = ((size_t)1 << log_n) << log_inner;
+    d.coset_shift = shift;
+    CK(ntt_execute(d, cur_stream()));
+    g_launches += (unsigned)ntt_plan_for((int)log_n, log_inner, batch).npass;
+    return 0;
+}
+
+int bb_ntt_device(uint32_t* d_data, uint32_t log_n, int dir) {
+    return run_ntt(d_data, d_data, log_n, 0, (size_t)1 << log_n, 1, dir, 1);
+}
+int bb_ntt_batch_device(uint32_t* d_data, uint32_t log_n, size_t batch, int dir) {
+    return run_ntt(d_data, d_data, log_n, 0, (size_t)1 << log_n, batch, dir, 1);
+}
+int bb_ntt_ext_device(uint32_t* d_data, uint32_t log_n, int dir) {
+    return run_ntt(d_data, d_data, log_n, 2, (size_t)1 << log_n, 1, dir, 1);
+}
+
+int bb_coset_fft_device(const uint32_t* d_coeffs, size_t n_coeffs, uint32_t log_size, uint32_t shift, int limbs,
+                        uint32_t* d_out) {
+    if ((limbs != 1 && limbs != 4) || shift == 0 || shift >= P) return note((int)cudaErrorInvalidValue);
+    size_t size = (size_t)1 << log_size;
+    size_t take = n_coeffs < size ? n_coeffs : size;  // resize() truncates, src/math/domain.rs:108-109
+    return run_ntt(d_coeffs, d_out, log_size, limbs == 4 ? 2 : 0, take, 1, 0, shift);
+}
+int bb_coset_ifft_device(uint32_t* d_evals, uint32_t log_size, uint32_t shift, int limbs) {
+    if ((limbs != 1 && limbs != 4) || shift == 0 || shift >= P) return note((int)cudaErrorInvalidValue);
+    return run_ntt(d_evals, d_evals, log_size, limbs == 4 ? 2 : 0, (size_t)1 << log_size, 1, 1, shift);
+}
+
+int bb_fri_fold_device(const uint32_t* d_evals, size_t m, uint32_t x0, const uint32_t beta[4], int limbs, uint32_t* d_out) {
+    if (!is_pow2(m) || (limbs != 1 && limbs != 4)) return note((int)cudaErrorInvalidValue);
+    CK(fri_fold_coset(d_evals, d_out, m, limbs, (int)log2_of(m), x0, beta, 1, 0, cur_stream()));
+    g_launches++;
+    return 0;
+}
+int bb_fri_fold_shard_device(const uint32_t* d_evals, size_t m_local, uint32_t log_m, uint32_t x0, const uint32_t beta[4],
+                             int limbs, uint32_t nranks, uint32_t rank, uint32_t* d_out) {
+    if ((limbs != 1 && limbs != 4) || nranks == 0 || rank >= nranks || m_local * nranks != ((size_t)1 << log_m))
+        return note((int)cudaErrorInvalidValue);
+    CK(fri_fold_coset(d_evals, d_out, m_local, limbs, (int)log_m, x0, beta, nranks, rank, cur_stream()));
+    g_launches++;
+    return 0;
+}
+int bb_fri_fold_xs_device(const uint32_t* d_evals, size_t m, const uint32_t* d_xs, const uint32_t beta[4], int limbs,
+                          uint32_t* d_out) {
+    if (limbs != 1 && limbs != 4) return note((int)cudaErrorInvalidValue);
+    CK(fri_fold_xs(d_evals, d_xs, d_out, m, limbs, beta, cur_stream()));
+    g_launches++;
+    return 0;
+}
+
+size_t bb_merkle_node_count(size_t nleaves) { return merkle_node_count(nleaves); }
+
+static int levels_of(size_t n) {
+    int l = 0;
+    while (n > 1) {
+        n = (n + 1) / 2;
+        l++;
+    }
+    return l;
+}
+
+static int root_to_host(const uint8_t* d_nodes, size_t n, uint8_t* root_out, cudaStream_t s) {
+    CK(cudaMemcpyAsync(root_out, d_nodes + 32 * (merkle_node_count(n) - 1), 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int bb_merkle_commit_device(const uint32_t* d_vals, int limbs, size_t n, const uint8_t* d_salts, uint8_t* d_nodes,
+                            uint8_t* root_out) {
+    CK(merkle_commit(d_vals, limbs, n, d_salts, d_nodes, cur_stream()));
+    g_launches += 1 + (unsigned)levels_of(n);
+    if (root_out) return root_to_host(d_nodes, n, root_out, cur_stream());
+    return 0;
+}
+int bb_merkle_build_bytes_device(const uint8_t* d_leaves, size_t n, size_t leaf_len, uint8_t* d_nodes, uint8_t* root_out) {
+    CK(merkle_build_bytes(d_leaves, n, leaf_len, d_nodes, cur_stream()));
+    g_launches += 1 + (unsigned)levels_of(n);
+    if (root_out) return root_to_host(d_nodes, n, root_out, cur_stream());
+    return 0;
+}
+int bb_merkle_open_device(const uint8_t* d_nodes, size_t nleaves, size_t index, uint8_t* path_out, uint8_t* pos_out,
+                          size_t* depth_out) {
+    uint8_t* d_path = nullptr;
+    CK(cudaMalloc(&d_path, 32 * 64));
+    size_t depth = 0;
+    int rc = merkle_open(d_nodes, nleaves, index, d_path, pos_out, &depth, cur_stream());
+    if (rc == 0 && depth > 0) {
+        g_launches++;
+        rc = (int)cudaMemcpyAsync(path_out, d_path, 32 * depth, cudaMemcpyDeviceToHost, cur_stream());
+    }
+    if (rc == 0) rc = (int)cudaStreamSynchronize(cur_stream());
+    cudaFree(d_path);
+    if (depth_out) *depth_out = depth;
+    return note(rc);
+}
+
+int bb_fri_commit_device(const uint32_t* d_layer0, size_t n, uint32_t shift, size_t final_size, int limbs,
+                         const uint8_t* d_salts, bb_challenge_fn challenge, void* user, const uint32_t* betas_in,
+                         uint32_t* d_layers, uint8_t* d_nodes, uint8_t* roots_out, size_t* folds_out) {
+    if (!is_pow2(n) || !is_pow2(final_size) || final_size > n || (limbs != 1 && limbs != 4) || shift == 0 || shift >= P)
+        return note((int)cudaErrorInvalidValue);
+    if (!challenge && !betas_in && n > final_size) return note((int)cudaErrorInvalidValue);
+    if (challenge && !d_nodes) return note((int)cudaErrorInvalidValue);  // a transcript needs roots
+    cudaStream_t s = cur_stream();
+    uint32_t* cur = d_layers;
+    if (d_layer0 != d_layers)
+        CK(cudaMemcpyAsync(d_layers, d_layer0, n * (size_t)limbs * 4, cudaMemcpyDeviceToDevice, s));
+    size_t cur_n = n, folds = 0;
+    uint32_t x0 = shift, log_m = log2_of(n);
+    const uint8_t* salt_ptr = d_salts;
+    uint8_t* node_ptr = d_nodes;
+    uint8_t root[32];
+    if (d_nodes) {  // layer 0 = DEEP evaluations, src/fibonacci.rs:204-211
+        CK(merkle_commit(cur, limbs, cur_n, cur_n == final_size ? nullptr : salt_ptr, node_ptr, s));
+        g_launches += 1 + (unsigned)levels_of(cur_n);
+        if (roots_out || challenge) {
+            CK(root_to_host(node_ptr, cur_n, root, s));
+            if (roots_out) memcpy(roots_out, root, 32);
+        }
+        if (salt_ptr && cur_n != final_size) salt_ptr += 16 * cur_n;
+        node_ptr += 32 * merkle_node_count(cur_n);
+    }
+    while (cur_n > final_size) {  // src/fibonacci.rs:222
+        uint32_t beta[4] = {0, 0, 0, 0};
+        if (challenge)
+            challenge(user, root, (uint32_t)folds, beta);  // absorb(root) happened for this root; squeeze beta (:223)
+        else
+            memcpy(beta, betas_in + (size_t)limbs * folds, sizeof(uint32_t) * (size_t)limbs);
+        uint32_t* next = cur + cur_n * (size_t)limbs;
+        CK(fri_fold_coset(cur, next, cur_n, limbs, (int)log_m, x0, beta, 1, 0, s));  // :225
+        g_launches++;
+        x0 = bb::mul(x0, x0);  // :228-231: x <- x^2
+        log_m--;
+        cur_n /= 2;
+        folds++;
+        if (d_nodes) {
+            const bool final_layer = (cur_n == final_size);  // :234-238
+            CK(merkle_commit(next, limbs, cur_n, final_layer ? nullptr : salt_ptr, node_ptr, s));
+            g_launches += 1 + (unsigned)levels_of(cur_n);
+            if (roots_out || challenge) {
+                CK(root_to_host(node_ptr, cur_n, root, s));
+                if (roots_out) memcpy(roots_out + 32 * folds, root, 32);
+            }
+            if (salt_ptr && !final_layer) salt_ptr += 16 * cur_n;
+            node_ptr += 32 * merkle_node_count(cur_n);
+        }
+        cur = next;
+    }
+    if (folds_out) *folds_out = folds;
+    return 0;
+}
+
+int bb_ntt_set_plan(uint32_t log_n, int npass, const int* log_rows, const int* log_cols) {
+    NttPlan pl{};
+    pl.npass = npass;
+    if (npass < 0 || npass > 3) return note((int)cudaErrorInvalidValue);
+    int sum = 0;
+    for (int i = 0; i < npass; i++) {
+        pl.lr[i] = log_rows[i];
+        pl.lc[i] = log_cols[i];
+        sum += log_rows[i];
+        if (!pass_launcher(pl.lr[i], pl.lc[i])) return note((int)cudaErrorInvalidValue);
+    }
+    if (npass > 0 && sum != (int)log_n) return note((int)cudaErrorInvalidValue);
+    ntt_plan_override((int)log_n, pl);
+    return 0;
+}
+int bb_ntt_get_plan(uint32_t log_n, int* log_rows, int* log_cols) {
+    NttPlan pl = ntt_plan_for((int)log_n, 0, 1);
+    for (int i = 0; i < pl.npass; i++) {
+        if (log_rows) log_rows[i] = pl.lr[i];
+        if (log_cols) log_cols[i] = pl.lc[i];
+    }
+    return pl.npass;
+}
+int bb_ntt_launches(uint32_t log_n) { return ntt_plan_for((int)log_n, 0, 1).npass; }
+unsigned long long bb_kernel_launch_count(void) { return g_launches.load(); }
+int bb_warmup(uint32_t log_n) {
+    if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
+    return note(engine_warmup((int)log_n));
+}
+void bb_release(void) { engine_release(); }
+
+}  // extern "C"
+
+// ================================================================== 3. host-pointer forms
+namespace {
+struct Staging {  // grow-on-demand device staging for the host-pointer entry points
+    uint64_t* d64 = nullptr;
+    size_t n64 = 0;
+    uint32_t* a32 = nullptr;
+    size_t na = 0;
+    uint32_t* b32 = nullptr;
+    size_t nb = 0;
+    uint8_t* bytes = nullptr;
+    size_t nbytes = 0;
+    uint8_t* nodes = nullptr;
+    size_t nnodes = 0;
+    std::mutex mu;
+};
+Staging g_stage;
+
+template <typename T>
+int grow(T** p, size_t* have, size_t want) {
+    if (*have >= want) return 0;
+    if (*p) {
+        cudaDeviceSynchronize();
+        cudaFree(*p);
+        *p = nullptr;
+        *have = 0;
+    }
+    int rc = (int)cudaMalloc((void**)p, want * sizeof(T));
+    if (rc == 0) *have = want;
+    return rc;
+}
+
+// upload `count` u64 values and narrow them into dst32
+int upload_narrow(const uint64_t* h, size_t count, uint32_t* dst32, cudaStream_t s) {
+    if (count == 0) return 0;
+    CK(grow(&g_stage.d64, &g_stage.n64, count));
+    CK(cudaMemcpyAsync(g_stage.d64, h, count * 8, cudaMemcpyHostToDevice, s));
+    narrow_kernel<<<conv_blocks(count), 256, 0, s>>>(g_stage.d64, dst32, count);
+    g_launches++;
+    return (int)cudaGetLastError();
+}
+int widen_download(const uint32_t* src32, size_t count, uint64_t* h, cudaStream_t s) {
+    if (count == 0) return 0;
+    CK(grow(&g_stage.d64, &g_stage.n64, count));
+    widen_kernel<<<conv_blocks(count), 256, 0, s>>>(src32, g_stage.d64, count);
+    g_launches++;
+    CK(cudaMemcpyAsync(h, g_stage.d64, count * 8, cudaMemcpyDeviceToHost, s));
+    return (int)cudaStreamSynchronize(s);
+}
+
+int domain_transform(const uint64_t* in, size_t n_in, size_t size, uint64_t shift, uint64_t* out, int limbs, bool inverse) {
+    if (!is_pow2(size) || log2_of(size) > (uint32_t)MAX_LOG_N) return note((int)cudaErrorInvalidValue);
+    if (inverse && n_in != size) return note((int)cudaErrorInvalidValue);  // assert_eq!, src/math/domain.rs:86
+    if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
+    std::lock_guard<std::mutex> lk(g_stage.mu);
+    cudaStream_t s = cur_stream();
+    size_t take = n_in < size ? n_in : size;
+    CK(grow(&g_stage.a32, &g_stage.na, (take ? take : 1) * (size_t)limbs));
+    CK(grow(&g_stage.b32, &g_stage.nb, size * (size_t)limbs));
+    const uint32_t sh = (uint32_t)(shift % P);
+    if (inverse) {
+        CK(upload_narrow(in, size * (size_t)limbs, g_stage.b32, s));
+        CK(bb_coset_ifft_device(g_stage.b32, log2_of(size), sh, limbs));
+    } else {
+        CK(upload_narrow(in, take * (size_t)limbs, g_stage.a32, s));
+        CK(bb_coset_fft_device(g_stage.a32, take, log2_of(size), sh, limbs, g_stage.b32));
+    }
+    return note(widen_download(g_stage.b32, size * (size_t)limbs, out, s));
+}
+
+int fold_host(const uint64_t* evals, size_t m, const uint64_t* xs, const uint64_t* beta, uint64_t* out, int limbs) {
+    if (m < 2 || (m & 1)) return note((int)cudaErrorInvalidValue);  // assert!, src/math/fri.rs:8,28
+    if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
+    std::lock_guard<std::mutex> lk(g_stage.mu);
+    cudaStream_t s = cur_stream();
+    const size_t half = m / 2;
+    CK(grow(&g_stage.a32, &g_stage.na, m * (size_t)limbs + half));
+    CK(grow(&g_stage.b32, &g_stage.nb, half * (size_t)limbs));
+    uint32_t* d_xs = g_stage.a32 + m * (size_t)limbs;
+    CK(upload_narrow(evals, m * (size_t)limbs, g_stage.a32, s));
+    CK(upload_narrow(xs, half, d_xs, s));
+    uint32_t b[4] = {0, 0, 0, 0};
+    for (int k = 0; k < limbs; k++) b[k] = (uint32_t)(beta[k] % P);
+    CK(bb_fri_fold_xs_device(g_stage.a32, m, d_xs, b, limbs, g_stage.b32));
+    return note(widen_download(g_stage.b32, half * (size_t)limbs, out, s));
+}
+}  // namespace
+
+extern "C" {
+
+int toyni_domain_fft(const uint64_t* coeffs, size_t n_coeffs, size_t size, uint64_t shift, uint64_t* evals_out) {
+    return domain_transform(coeffs, n_coeffs, size, shift, evals_out, 1, false);
+}
+int toyni_domain_ifft(const uint64_t* evals, size_t size, uint64_t shift, uint64_t* coeffs_out) {
+    return domain_transform(evals, size, size, shift, coeffs_out, 1, true);
+}
+int toyni_domain_fft_ext(const uint64_t* coeffs, size_t n_coeffs, size_t size, uint64_t shift, uint64_t* evals_out) {
+    return domain_transform(coeffs, n_coeffs, size, shift, evals_out, 4, false);
+}
+int toyni_domain_ifft_ext(const uint64_t* evals, size_t size, uint64_t shift, uint64_t* coeffs_out) {
+    return domain_transform(evals, size, size, shift, coeffs_out, 4, true);
+}
+int toyni_fri_fold(const uint64_t* evals, size_t m, const uint64_t* xs, uint64_t beta, uint64_t* out) {
+    return fold_host(evals, m, xs, &beta, out, 1);
+}
+int toyni_fri_fold_ext(const uint64_t* evals, size_t m, const uint64_t* xs, const uint64_t beta[4], uint64_t* out) {
+    return fold_host(evals, m, xs, beta, out, 4);
+}
+int toyni_merkle_commit(const uint64_t* values, size_t n, int limbs, const uint8_t* salts, uint8_t* nodes_out,
+                        uint8_t root_out[32]) {
+    if (n == 0 || (limbs != 1 && limbs != 4)) return note((int)cudaErrorInvalidValue);
+    if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
+    std::lock_guard<std::mutex> lk(g_stage.mu);
+    cudaStream_t s = cur_stream();
+    const size_t count = merkle_node_count(n);
+    CK(grow(&g_stage.a32, &g_stage.na, n * (size_t)limbs));
+    CK(grow(&g_stage.nodes, &g_stage.nnodes, count * 32));
+    CK(upload_narrow(values, n * (size_t)limbs, g_stage.a32, s));
+    uint8_t* d_salts = nullptr;
+    if (salts) {
+        CK(grow(&g_stage.bytes, &g_stage.nbytes, n * 16));
+        CK(cudaMemcpyAsync(g_stage.bytes, salts, n * 16, cudaMemcpyHostToDevice, s));
+        d_salts = g_stage.bytes;
+    }
+    CK(bb_merkle_commit_device(g_stage.a32, limbs, n, d_salts, g_stage.nodes, root_out));
+    if (nodes_out) CK(cudaMemcpyAsync(nodes_out, g_stage.nodes, count * 32, cudaMemcpyDeviceToHost, s));
+    return note((int)cudaStreamSynchronize(s));
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// FRI layer folding on the device.
+//   out[i] = (a+b)/2 + (a-b)/2 * beta * x_i^-1,  a = evals[i], b = evals[i+half]
+// follows src/math/fri.rs:27-48 (base field) and :7-25 (extension field).  The reference spends one Fermat
+// inverse (61 modmuls) per output; here x_i = x0 * omega_m^i is generated on chip from the cached
+// omega_N^-t power table, so a fold reads 2 values, writes 1 and needs no xs array.
+// A general-xs form (arbitrary evaluation points, per-element Fermat inverse) keeps the reference signature.
+#include "fri_fold.cuh"
+
+#include "ntt_pass.cuh"
+
+namespace bb {
+
+// exponent of omega_N^-1 for local index t:  ((t * idx_mul + idx_add) << shift)
+struct FoldIdx {
+    uint32_t idx_mul, idx_add, shift;
+};
+
+__global__ void __launch_bounds__(256) fold_base_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                        size_t half, PowTable winv, FoldIdx fi, uint32_t c_m) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    uint32_t a = in[i], b = in[i + half];
+    uint32_t tw = monty_mul(pow_lookup(winv, ((uint32_t)i * fi.idx_mul + fi.idx_add) << fi.shift), c_m);  // Montgomery form
+    out[i] = add(halve(add(a, b)), monty_mul(sub(a, b), tw));
+}
+
+__global__ void __launch_bounds__(256) fold_ext_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t half,
+                                                       PowTable winv, FoldIdx fi, Ext c_m) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    uint4 av = in[i], bv = in[i + half];
+    Ext a{{av.x, av.y, av.z, av.w}}, b{{bv.x, bv.y, bv.z, bv.w}};
+    uint32_t tw = pow_lookup(winv, ((uint32_t)i * fi.idx_mul + fi.idx_add) << fi.shift);
+    Ext g;  // Montgomery form of (beta/2 * x0^-1) * omega^-i
+#pragma unroll
+    for (int k = 0; k < 4; k++) g.c[k] = monty_mul(c_m.c[k], tw);
+    Ext s = ext_add(a, b), d = ext_sub(a, b);
+    Ext t = ext_mul_monty(d, g);
+    uint4 r;
+    r.x = add(halve(s.c[0]), t.c[0]);
+    r.y = add(halve(s.c[1]), t.c[1]);
+    r.z = add(halve(s.c[2]), t.c[2]);
+    r.w = add(halve(s.c[3]), t.c[3]);
+    out[i] = r;
+}
+
+// general evaluation points: x^-1 by Fermat, exactly as src/babybear.rs:111-114 (but in Montgomery form)
+__device__ __forceinline__ uint32_t inv_monty_dev(uint32_t x) {  // returns Montgomery form of x^-1
+    uint32_t b = to_monty(x), r = R_MOD_P;
+    uint32_t e = P - 2;
+#pragma unroll 1
+    while (e) {
+        if (e & 1u) r = monty_mul(r, b);
+        b = monty_mul(b, b);
+        e >>= 1;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256) fold_base_xs_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ xs,
+                                                           uint32_t* __restrict__ out, size_t half, uint32_t halfbeta_m) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    uint32_t a = in[i], b = in[i + half];
+    uint32_t tw = monty_mul(inv_monty_dev(xs[i]), halfbeta_m);
+    out[i] = add(halve(add(a, b)), monty_mul(sub(a, b), tw));
+}
+
+__global__ void __launch_bounds__(256) fold_ext_xs_kernel(const uint4* __restrict__ in, const uint32_t* __restrict__ xs,
+                                                          uint4* __restrict__ out, size_t half, Ext halfbeta_m) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    uint4 av = in[i], bv = in[i + half];
+    Ext a{{av.x, av.y, av.z, av.w}}, b{{bv.x, bv.y, bv.z, bv.w}};
+    uint32_t xi = inv_monty_dev(xs[i]);
+    Ext g;
+#pragma unroll
+    for (int k = 0; k < 4; k++) g.c[k] = monty_mul(halfbeta_m.c[k], xi);
+    Ext s = ext_add(a, b), d = ext_sub(a, b);
+    Ext t = ext_mul_monty(d, g);
+    uint4 r;
+    r.x = add(halve(s.c[0]), t.c[0]);
+    r.y = add(halve(s.c[1]), t.c[1]);
+    r.z = add(halve(s.c[2]), t.c[2]);
+    r.w = add(halve(s.c[3]), t.c[3]);
+    out[i] = r;
+}
+
+static inline unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
+
+int fri_fold_coset(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int limbs, int log_m_global, uint32_t x0,
+                   const uint32_t beta[4], uint32_t idx_mul, uint32_t idx_add, cudaStream_t s) {
+    if (m_local < 2 || (m_local & 1) || log_m_global < 1 || log_m_global > MAX_LOG_N || x0 == 0) return (int)cudaErrorInvalidValue;
+    PowTable winv;
+    // omega_m^-t table; shared with the inverse NTT of the same size
+    int rc = engine_pow_table(bb::inv(root_of_unity(log_m_global)), log_m_global, 1u, &winv);
+    if (rc) return rc;
+    const size_t half = m_local / 2;
+    const uint32_t hx = bb::mul(HALF, bb::inv(x0));  // (1/2) * x0^-1
+    FoldIdx fi{idx_mul, idx_add, 0};
+    if (limbs == 1) {
+        fold_base_kernel<<<blocks_for(half), 256, 0, s>>>(d_in, d_out, half, winv, fi, to_monty(bb::mul(hx, beta[0])));
+    } else {
+        Ext c;
+        for (int k = 0; k < 4; k++) c.c[k] = to_monty(bb::mul(hx, beta[k]));
+        fold_ext_kernel<<<blocks_for(half), 256, 0, s>>>((const uint4*)d_in, (uint4*)d_out, half, winv, fi, c);
+    }
+    return (int)cudaGetLastError();
+}
+
+int fri_fold_xs(const uint32_t* d_in, const uint32_t* d_xs, uint32_t* d_out, size_t m, int limbs, const uint32_t beta[4],
+                cudaStream_t s) {
+    if (m < 2 || (m & 1)) return (int)cudaErrorInvalidValue;
+    const size_t half = m / 2;
+    if (limbs == 1) {
+        fold_base_xs_kernel<<<blocks_for(half), 256, 0, s>>>(d_in, d_xs, d_out, half, to_monty(bb::mul(HALF, beta[0])));
+    } else {
+        Ext c;
+        for (int k = 0; k < 4; k++) c.c[k] = to_monty(bb::mul(HALF, beta[k]));
+        fold_ext_xs_kernel<<<blocks_for(half), 256, 0, s>>>((const uint4*)d_in, d_xs, (uint4*)d_out, half, c);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace bb

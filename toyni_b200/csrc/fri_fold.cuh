@@ -1,0 +1,19 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "ntt_engine.cuh"
+
+namespace bb {
+// Fold a layer whose evaluation points are x_i = x0 * omega_m^i (m = 2^log_m_global).  `d_in` holds m_local
+// values of `limbs` u32 each; local index t stands for global index t*idx_mul + idx_add (1, 0 on one GPU;
+// G, rank for the cyclic multi-GPU layout).  Pairs are (t, t + m_local/2).
+int fri_fold_coset(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int limbs, int log_m_global, uint32_t x0,
+                   const uint32_t beta[4], uint32_t idx_mul, uint32_t idx_add, cudaStream_t s);
+// Reference signature: arbitrary evaluation points xs[0..m/2) on the device.
+int fri_fold_xs(const uint32_t* d_in, const uint32_t* d_xs, uint32_t* d_out, size_t m, int limbs, const uint32_t beta[4],
+                cudaStream_t s);
+// cached g^t tables (shared with the NTT engine)
+int engine_pow_table(uint32_t g, int log_total, uint32_t scale, PowTable* out);
+}  // namespace bb

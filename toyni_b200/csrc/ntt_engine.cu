@@ -1,0 +1,386 @@
+// NTT engine: on-device twiddle generation + cache, pass planner, executor.  See ntt_engine.cuh.
+#include "ntt_engine.cuh"
+
+#include "fri_fold.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace bb {
+
+// ------------------------------------------------------------------ table generation kernels
+__device__ __forceinline__ uint32_t monty_pow_dev(uint32_t g_m, uint32_t e) {
+    uint32_t r = R_MOD_P, b = g_m;
+    while (e) {
+        if (e & 1u) r = monty_mul(r, b);
+        b = monty_mul(b, b);
+        e >>= 1;
+    }
+    return r;
+}
+
+// out[i] = g^i * scale, Montgomery form
+__global__ void gen_pow_kernel(uint32_t* out, uint32_t count, uint32_t g_m, uint32_t scale_m) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = monty_mul(monty_pow_dev(g_m, i), scale_m);
+}
+
+// out[i] = (w, floor(w 2^32 / p)) with w = g^i, plain form
+__global__ void gen_shoup_kernel(uint2* out, uint32_t count, uint32_t g_m) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        uint32_t w = from_monty(monty_pow_dev(g_m, i));
+        out[i] = make_uint2(w, shoup_companion(w));
+    }
+}
+
+// ------------------------------------------------------------------ per-device state
+struct PowTab {
+    uint32_t* lo = nullptr;
+    uint32_t* hi = nullptr;
+    uint32_t lo_bits = 0;
+};
+
+struct DeviceState {
+    uint2* tw[2] = {nullptr, nullptr};  // omega_4096^(+-i), i < 2048
+    uint2 tw16[2][8];
+    std::map<std::tuple<uint32_t, int, uint32_t>, PowTab> pow_tabs;  // (g, log_total, scale) -> tables
+    uint32_t* scratch = nullptr;
+    size_t scratch_words = 0;
+    bool ready = false;
+};
+
+static std::mutex g_mu;
+static std::map<int, DeviceState> g_states;
+static std::map<int, NttPlan> g_plan_override;
+
+#define BB_CK(x)                          \
+    do {                                  \
+        cudaError_t e_ = (x);             \
+        if (e_ != cudaSuccess) return (int)e_; \
+    } while (0)
+
+static int state_get(DeviceState** out) {
+    int dev = 0;
+    BB_CK(cudaGetDevice(&dev));
+    DeviceState& st = g_states[dev];
+    if (!st.ready) {
+        for (int inv = 0; inv < 2; inv++) {
+            uint32_t w = root_of_unity(LOG_TW);
+            if (inv) w = bb::inv(w);
+            BB_CK(cudaMalloc(&st.tw[inv], sizeof(uint2) << (LOG_TW - 1)));
+            gen_shoup_kernel<<<(1 << (LOG_TW - 1)) / 256, 256>>>(st.tw[inv], 1u << (LOG_TW - 1), to_monty(w));
+            BB_CK(cudaGetLastError());
+            uint32_t w16 = root_of_unity(4);
+            if (inv) w16 = bb::inv(w16);
+            uint32_t cur = 1;
+            for (int i = 0; i < 8; i++) {
+                st.tw16[inv][i] = make_uint2(cur, shoup_companion(cur));
+                cur = bb::mul(cur, w16);
+            }
+        }
+        BB_CK(cudaDeviceSynchronize());
+        st.ready = true;
+    }
+    *out = &st;
+    return 0;
+}
+
+// tables for g^t, t < 2^log_total, every entry pre-multiplied by `scale` (through the lo table)
+static int pow_table_get(DeviceState& st, uint32_t g, int log_total, uint32_t scale, PowTable* out) {
+    auto key = std::make_tuple(g, log_total, scale);
+    auto it = st.pow_tabs.find(key);
+    if (it == st.pow_tabs.end()) {
+        PowTab t;
+        t.lo_bits = (uint32_t)((log_total + 1) / 2);
+        uint32_t n_lo = 1u << t.lo_bits, n_hi = 1u << (log_total - (int)t.lo_bits);
+        BB_CK(cudaMalloc(&t.lo, sizeof(uint32_t) * n_lo));
+        BB_CK(cudaMalloc(&t.hi, sizeof(uint32_t) * n_hi));
+        gen_pow_kernel<<<(n_lo + 255) / 256, 256>>>(t.lo, n_lo, to_monty(g), to_monty(scale));
+        gen_pow_kernel<<<(n_hi + 255) / 256, 256>>>(t.hi, n_hi, to_monty(bb::pow(g, n_lo)), R_MOD_P);
+        BB_CK(cudaGetLastError());
+        // generated on the legacy default stream: make them visible to any (possibly non-blocking) stream
+        BB_CK(cudaDeviceSynchronize());
+        it = st.pow_tabs.emplace(key, t).first;
+    }
+    out->lo = it->second.lo;
+    out->hi = it->second.hi;
+    out->lo_bits = it->second.lo_bits;
+    return 0;
+}
+
+static int scratch_get(DeviceState& st, size_t words, uint32_t** out) {
+    if (st.scratch_words < words) {
+        if (st.scratch) {
+            BB_CK(cudaDeviceSynchronize());
+            BB_CK(cudaFree(st.scratch));
+            st.scratch = nullptr;
+            st.scratch_words = 0;
+        }
+        BB_CK(cudaMalloc(&st.scratch, words * sizeof(uint32_t)));
+        st.scratch_words = words;
+    }
+    *out = st.scratch;
+    return 0;
+}
+
+int engine_pow_table(uint32_t g, int log_total, uint32_t scale, PowTable* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState* st;
+    int rc = state_get(&st);
+    if (rc) return rc;
+    return pow_table_get(*st, g, log_total, scale, out);
+}
+
+size_t engine_scratch_bytes() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto it = g_states.find(dev);
+    return it == g_states.end() ? 0 : it->second.scratch_words * sizeof(uint32_t);
+}
+
+void engine_release() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto it = g_states.find(dev);
+    if (it == g_states.end()) return;
+    cudaDeviceSynchronize();
+    DeviceState& st = it->second;
+    for (int i = 0; i < 2; i++) cudaFree(st.tw[i]);
+    for (auto& kv : st.pow_tabs) {
+        cudaFree(kv.second.lo);
+        cudaFree(kv.second.hi);
+    }
+    cudaFree(st.scratch);
+    g_states.erase(it);
+}
+
+// ------------------------------------------------------------------ planner
+static int max_lc_for(int lr) { return lr >= 12 ? 3 : (lr == 11 ? 4 : 5); }
+
+static int pick_lc(int lr, int want) {  // largest built LC <= want (built: 0,2,3,4,5 within the smem limit)
+    int lc = want < max_lc_for(lr) ? want : max_lc_for(lr);
+    if (lc == 1) lc = 0;
+    if (lc < 0) lc = 0;
+    return lc;
+}
+
+static int ceil_log2(size_t v) {
+    int l = 0;
+    while (((size_t)1 << l) < v) l++;
+    return l;
+}
+
+void ntt_plan_override(int log_n, const NttPlan& plan) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (plan.npass == 0)
+        g_plan_override.erase(log_n);
+    else
+        g_plan_override[log_n] = plan;
+}
+
+static NttPlan plan_locked(int log_n, int log_inner, size_t batch) {
+    auto it = g_plan_override.find(log_n);
+    if (it != g_plan_override.end()) return it->second;
+    NttPlan pl;
+    memset(&pl, 0, sizeof pl);
+    if (log_n <= MAX_LR) {
+        pl.npass = 1;
+        pl.lr[0] = log_n;
+        if (log_inner > 0) {
+            pl.lc[0] = pick_lc(log_n, log_inner);
+        } else {
+            // columns are the vectors of the batch: aim for ~4096-element tiles
+            int want = MAX_LR - log_n;
+            int lb = ceil_log2(batch);
+            pl.lc[0] = pick_lc(log_n, want < lb ? want : lb);
+        }
+        return pl;
+    }
+    if (log_n <= 2 * MAX_LR) {
+        pl.npass = 2;
+        pl.lr[0] = (log_n + 1) / 2;
+        pl.lr[1] = log_n - pl.lr[0];
+    } else {
+        pl.npass = 3;
+        pl.lr[0] = (log_n + 2) / 3;
+        pl.lr[1] = (log_n - pl.lr[0] + 1) / 2;
+        pl.lr[2] = log_n - pl.lr[0] - pl.lr[1];
+    }
+    for (int i = 0; i < pl.npass; i++) {
+        // tiles of about 8192 elements keep several CTAs resident per SM; never below 8 columns (32-byte segments)
+        int want = 13 - pl.lr[i];
+        if (want < 3) want = 3;
+        pl.lc[i] = pick_lc(pl.lr[i], want);
+    }
+    return pl;
+}
+
+NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return plan_locked(log_n, log_inner, batch);
+}
+
+// ------------------------------------------------------------------ executor
+int engine_warmup(int log_n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState* st;
+    int rc = state_get(&st);
+    if (rc) return rc;
+    if (log_n > MAX_LR) {
+        uint32_t* s;
+        rc = scratch_get(*st, (size_t)1 << log_n, &s);
+        if (rc) return rc;
+        for (int inv = 0; inv < 2; inv++) {
+            uint32_t w = root_of_unity(log_n);
+            PowTable t;
+            if (inv) {
+                w = bb::inv(w);
+                rc = pow_table_get(*st, w, log_n, bb::inv((uint32_t)(((uint64_t)1 << log_n) % P)), &t);
+                if (rc) return rc;
+            }
+            rc = pow_table_get(*st, w, log_n, 1, &t);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+int ntt_execute(const NttDesc& d, cudaStream_t stream) {
+    if (d.log_n < 0 || d.log_n > MAX_LOG_N) return (int)cudaErrorInvalidValue;
+    if (d.batch == 0) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState* st;
+    int rc = state_get(&st);
+    if (rc) return rc;
+
+    const int inv = d.inverse ? 1 : 0;
+    const size_t n = (size_t)1 << d.log_n;
+    const size_t inner = (size_t)1 << d.log_inner;
+    const bool coset = d.coset_shift > 1;
+    const NttPlan pl = plan_locked(d.log_n, d.log_inner, d.batch);
+
+    const uint32_t n_inv = bb::inv((uint32_t)(n % P));
+    uint32_t omega = root_of_unity(d.log_n);
+    if (inv) omega = bb::inv(omega);
+
+    PowTable tw_first{}, tw_rest{};
+    if (pl.npass > 1) {
+        // inverse transforms fold n^-1 into the first inter-pass twiddle unless the coset epilogue carries it
+        uint32_t scale_first = (inv && !coset) ? n_inv : 1u;
+        rc = pow_table_get(*st, omega, d.log_n, scale_first, &tw_first);
+        if (rc) return rc;
+        if (pl.npass > 2) {
+            rc = pow_table_get(*st, omega, d.log_n, 1u, &tw_rest);
+            if (rc) return rc;
+        }
+    }
+    PowTable coset_tab{};
+    if (coset) {
+        if (!inv)
+            rc = pow_table_get(*st, d.coset_shift, d.log_n, 1u, &coset_tab);
+        else
+            rc = pow_table_get(*st, bb::inv(d.coset_shift), d.log_n, n_inv, &coset_tab);
+        if (rc) return rc;
+    }
+
+    uint32_t* scratch = nullptr;
+    if (pl.npass > 1) {
+        rc = scratch_get(*st, n * inner * d.batch, &scratch);
+        if (rc) return rc;
+    }
+
+    const bool transposed = (pl.npass == 1 && d.log_inner == 0);
+    if (transposed && d.batch > 1 && (d.batch_stride_out != n)) return (int)cudaErrorInvalidValue;
+
+    int log_p = 0;  // log2(R_1 ... R_{i-1})
+    for (int i = 0; i < pl.npass; i++) {
+        const int lr = pl.lr[i], lc = pl.lc[i];
+        const bool first = (i == 0), last = (i == pl.npass - 1);
+        PassLaunchFn fn = pass_launcher(lr, lc);
+        if (!fn) return (int)cudaErrorInvalidConfiguration;
+
+        PassParams p;
+        memset(&p, 0, sizeof p);
+        // buffer chain: 1 pass in->out; 2 passes in->scratch->out; 3 passes in->scratch->out->out
+        const uint32_t* src;
+        uint32_t* dst;
+        size_t src_bs, dst_bs;
+        if (first) {
+            src = d.in;
+            src_bs = d.batch_stride_in;
+        } else if (i == 1) {
+            src = scratch;
+            src_bs = n * inner;
+        } else {
+            src = d.out;
+            src_bs = d.batch_stride_out;
+        }
+        if (last || i == 1) {
+            dst = d.out;
+            dst_bs = d.batch_stride_out;
+        } else {
+            dst = scratch;
+            dst_bs = n * inner;
+        }
+        p.in = src;
+        p.out = dst;
+        p.tw = st->tw[inv];
+        p.log_tw = LOG_TW;
+        memcpy(p.tw16, st->tw16[inv], sizeof p.tw16);
+        p.log_inner = (uint32_t)d.log_inner;
+        p.n_in_limit = first ? (unsigned long long)d.n_in * inner : ~0ull;
+
+        dim3 grid;
+        if (transposed) {
+            p.transposed = 1;
+            p.ncols = (uint32_t)d.batch;
+            p.in_row_stride = 1;
+            p.in_col_stride = d.batch_stride_in;
+            p.log_pfull = 0;
+            p.in_batch_stride = p.out_batch_stride = 0;
+            p.n_in_limit = d.n_in;
+            grid = dim3((unsigned)((d.batch + ((size_t)1 << lc) - 1) >> lc), 1, 1);
+        } else {
+            const size_t ncols = (n >> lr) * inner;
+            p.transposed = 0;
+            p.ncols = (uint32_t)ncols;
+            p.in_row_stride = ncols;
+            p.in_col_stride = 1;
+            p.log_pfull = (uint32_t)(log_p + d.log_inner);
+            p.in_batch_stride = src_bs;
+            p.out_batch_stride = dst_bs;
+            grid = dim3((unsigned)((ncols + ((size_t)1 << lc) - 1) >> lc), (unsigned)d.batch, 1);
+        }
+
+        if (first && coset && !inv) {
+            p.pro_mode = PRO_INIDX;
+            p.pro = coset_tab;
+        }
+        if (!last) {
+            p.epi_mode = EPI_TWIDDLE;
+            p.epi = first ? tw_first : tw_rest;
+            p.epi_shift = (uint32_t)log_p;
+        } else if (coset && inv) {
+            p.epi_mode = EPI_OUTIDX;
+            p.epi = coset_tab;
+        } else if (inv && pl.npass == 1) {
+            p.epi_mode = EPI_CONST;
+            p.epi_const = to_monty(n_inv);
+        } else {
+            p.epi_mode = EPI_NONE;
+        }
+        fn(p, grid, stream);
+        BB_CK(cudaGetLastError());
+        log_p += lr;
+    }
+    return 0;
+}
+
+}  // namespace bb

@@ -1,0 +1,46 @@
+// Host-side NTT engine: per-device twiddle cache, pass planner and executor.
+// Replaces NttCtx / ntt_ctx_create / build_twiddles_device (cuda/ntt_kernel.cu:160-242): twiddles are
+// generated on the device, are O(sqrt n) instead of 2(n-1) words, and are shared by every context.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "ntt_pass.cuh"
+
+namespace bb {
+
+constexpr int MAX_LOG_N = 27;  // two-adicity of BabyBear, src/babybear.rs:119
+constexpr int MAX_LR = 12;     // largest in-tile transform
+constexpr int LOG_TW = 12;     // master Shoup table covers omega_4096
+
+struct NttPlan {
+    int npass;
+    int lr[3];
+    int lc[3];
+};
+
+struct NttDesc {
+    int log_n;              // transform length 2^log_n
+    int log_inner;          // interleaved columns per element (0 plain, 2 for AoS Ext)
+    bool inverse;
+    const uint32_t* in;     // device
+    uint32_t* out;          // device (may equal `in`)
+    size_t n_in;            // valid input elements per vector (<= n); the rest read as zero
+    size_t batch;           // independent contiguous vectors
+    size_t batch_stride_in;   // in elements*inner (u32 units)
+    size_t batch_stride_out;
+    uint32_t coset_shift;   // 0 or 1: none.  forward: x[i] *= s^i first; inverse: y[k] *= s^-k afterwards
+};
+
+// All functions return cudaError_t as int (0 = success) and never synchronise the stream.
+int ntt_execute(const NttDesc& d, cudaStream_t stream);
+NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch);
+// Tuning hook: override the planner for one size ("lr1,lr2[,lr3]/lc1,lc2[,lc3]"); npass=0 clears it.
+void ntt_plan_override(int log_n, const NttPlan& plan);
+PassLaunchFn pass_launcher(int lr, int lc);  // nullptr if that tile shape is not built
+int engine_warmup(int log_n);                // build tables / scratch ahead of time
+size_t engine_scratch_bytes();
+void engine_release();                       // free every cached device allocation on the current device
+
+}  // namespace bb
