@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py — BabyBear NTT throughput on B200 (BASELINE.json metric: "BabyBear NTT Gelem/s @2^24").
+
+One step = one forward 2^24-point NTT (the configuration the metric is quoted on, BASELINE.json configs[1]) on
+synthetic random field elements.  `value` is device-resident throughput (inputs already in HBM, CUDA-event
+timed, rotating over more buffers than fit in L2); `e2e` is the same transform through the reference-facing
+C ABI (`ntt_run_inplace`, src/ntt.rs:108) on pinned HOST u64 buffers with both PCIe copies inside the timed
+region.  With --gpus N every rank transforms its own column (independent NTTs shard with no collective: weak
+scaling); --workload fourstep27 runs ONE 2^27 transform sharded over the ranks with an all-to-all instead.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ntt24|fourstep27]
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "babybear_ntt_2^24_throughput"
+UNIT = "Gelem/s"
+LOG_N = 24
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def _traffic(log_n):
+    """dram bytes per transform from the committed ncu capture (profiles/ncu_traffic.json), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(f"ntt_2^{log_n}_dram_bytes_per_transform")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path (src/ntt.rs:24-53).  No Rust toolchain exists in this
+    image, so it is the C port in oracle/ (same loop order, same u128 % p multiply), with every host thread the
+    algorithm can use (independent butterfly groups per stage over OpenMP)."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    n = 1 << LOG_N
+    x = O.random_field(n)
+    for _ in range(args.warmup):
+        O.ntt_inplace(x, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.ntt_inplace(x, threads=cores)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "forward BabyBear NTT, n=2^24, one vector per step (BASELINE configs[1])",
+                   "note": "reference CPU algorithm (src/ntt.rs:24-53) as the C port oracle/toyni_oracle.c; "
+                           "the reference is Rust and no Rust toolchain exists here"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} forward NTTs of 2^24 after {args.warmup} warm-ups, OpenMP over {cores} threads"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from toyni_b200 import device as D
+    from toyni_b200 import ntt as host_ntt
+    from toyni_b200.lib import lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = lib()
+    if not L.bb_device_ok():
+        raise SystemExit("bench.py needs a compute-capability 10.x device (no CPU fallback)")
+    n = 1 << LOG_N
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "fourstep27":
+        from toyni_b200 import multigpu
+        return multigpu.bench_fourstep(args, rank, world, dev)
+
+    # Inputs: NB distinct device-resident vectors (NB * 64 MiB > the 126 MB L2), uniformly random canonical values.
+    NB = 4
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x70796E69 + rank)
+    bufs = [torch.randint(0, 2013265921, (n,), dtype=torch.int32, device=dev, generator=g) for _ in range(NB)]
+    L.bb_warmup(LOG_N)
+
+    def step(i):
+        D.ntt_(bufs[i % NB], inverse=False)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.bb_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_step = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record()
+    for i in range(args.steps):
+        per_step[i][0].record()
+        step(i)
+        per_step[i][1].record()
+    ev1.record()
+    barrier()
+    launches = L.bb_kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in per_step)  # one transform = its pass kernels back to back
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * n * args.steps / (ms_total * 1e-3) / 1e9
+
+    # ---- end to end through the reference-facing C ABI on pinned host buffers (every rank, max over ranks)
+    host = torch.empty(n, dtype=torch.int64).pin_memory()
+    hv = host.numpy().view(np.uint64)
+    hv[:] = (np.arange(n, dtype=np.uint64) * np.uint64(7) + np.uint64(3)) % np.uint64(2013265921)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        host_ntt.ntt_cuda(hv)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_ntt.ntt_cuda(hv)  # H2D (u64) + narrow + NTT passes + widen + D2H (u64), synchronous
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * n * e2e_steps / float(t.item()) / 1e9
+
+    if rank != 0:
+        return
+    peak, peak_kind = _peaks()
+    npass = L.bb_ntt_launches(LOG_N)
+    achieved = 8.0 * n / (kernel_ms * 1e-3) / 1e9  # algorithmic bytes: 4 B read + 4 B written per element per transform
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "forward BabyBear NTT, n=2^24, one vector per GPU per step (BASELINE configs[1])",
+                   "l2": f"inputs rotate over {NB} x 64 MiB device buffers (larger than the 126 MB L2)",
+                   "kernels_per_transform": npass, "parallelism": f"independent columns x{world}, no collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": _traffic(LOG_N), "peak_source": peak_kind,
+                     "note": "algorithmic 8 B/element over the transform's pass kernels (CUDA events around each transform); "
+                             "the kernels are INT32-pipe bound, see DESIGN.md and profiles/"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+                "steps": e2e_steps, "api": "ntt_run_inplace (src/ntt.rs:108) on pinned host u64"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        x = O.random_field(n)
+        t0 = time.perf_counter()
+        O.ntt_inplace(x, threads=1)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "one forward NTT of 2^24, single thread (the reference has no threading), "
+                                          "C port of src/ntt.rs:24-53"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ntt24", choices=["ntt24", "fourstep27"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

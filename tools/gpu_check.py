@@ -4,7 +4,8 @@ import numpy as np
 import torch
 sys.path.insert(0, ".")
 from oracle import oracle as O
-from toyni_b200 import device as D, lib as L
+from toyni_b200 import device as D
+from toyni_b200.lib import lib as _lib
 
 def check_ntt(log_n, inverse=False):
     n = 1 << log_n
@@ -27,6 +28,6 @@ if __name__ == "__main__":
             t0 = time.time()
             ok = check_ntt(log_n, inv)
             allok &= ok
-            print(f"ntt log_n={log_n:2d} inv={int(inv)} {'OK' if ok else 'FAIL'} plan={[L.lib().bb_ntt_launches(log_n)]} ({time.time()-t0:.2f}s)", flush=True)
+            print(f"ntt log_n={log_n:2d} inv={int(inv)} {'OK' if ok else 'FAIL'} plan={[_lib().bb_ntt_launches(log_n)]} ({time.time()-t0:.2f}s)", flush=True)
     print("ALL OK" if allok else "FAILURES")
     sys.exit(0 if allok else 1)

@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -57,6 +58,7 @@ struct DeviceState {
 static std::mutex g_mu;
 static std::map<int, DeviceState> g_states;
 static std::map<int, NttPlan> g_plan_override;
+static bool g_force_scalar = false;  // test hook: run every pass on the scalar kernel
 
 #define BB_CK(x)                          \
     do {                                  \
@@ -222,6 +224,8 @@ static NttPlan plan_locked(int log_n, int log_inner, size_t batch) {
     return pl;
 }
 
+void engine_force_scalar(bool on) { g_force_scalar = on; }
+
 NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch) {
     std::lock_guard<std::mutex> lk(g_mu);
     return plan_locked(log_n, log_inner, batch);
@@ -303,8 +307,6 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
     for (int i = 0; i < pl.npass; i++) {
         const int lr = pl.lr[i], lc = pl.lc[i];
         const bool first = (i == 0), last = (i == pl.npass - 1);
-        PassLaunchFn fn = pass_launcher(lr, lc);
-        if (!fn) return (int)cudaErrorInvalidConfiguration;
 
         PassParams p;
         memset(&p, 0, sizeof p);
@@ -376,6 +378,13 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
         } else {
             p.epi_mode = EPI_NONE;
         }
+        // vectorised kernel whenever chunks of four columns stay whole; scalar kernel otherwise
+        PassLaunchFn fn = nullptr;
+        const bool aligned = ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) && (src_bs % 4 == 0) && (dst_bs % 4 == 0);
+        if (!transposed && lc >= 2 && aligned && p.log_pfull != 1 && (p.ncols & ((1u << lc) - 1u)) == 0 && !g_force_scalar)
+            fn = pass_launcher_v4(lr, lc);
+        if (!fn) fn = pass_launcher(lr, lc);
+        if (!fn) return (int)cudaErrorInvalidConfiguration;
         fn(p, grid, stream);
         BB_CK(cudaGetLastError());
         log_p += lr;

@@ -38,7 +38,9 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream);
 NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch);
 // Tuning hook: override the planner for one size ("lr1,lr2[,lr3]/lc1,lc2[,lc3]"); npass=0 clears it.
 void ntt_plan_override(int log_n, const NttPlan& plan);
-PassLaunchFn pass_launcher(int lr, int lc);  // nullptr if that tile shape is not built
+PassLaunchFn pass_launcher(int lr, int lc);     // scalar kernel; nullptr if that tile shape is not built
+PassLaunchFn pass_launcher_v4(int lr, int lc);  // vectorised kernel (LC >= 2)
+void engine_force_scalar(bool on);            // test hook
 int engine_warmup(int log_n);                // build tables / scratch ahead of time
 size_t engine_scratch_bytes();
 void engine_release();                       // free every cached device allocation on the current device
