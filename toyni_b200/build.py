@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-diag-suppress", "186"]
+         "-Xcompiler", "-fPIC", "-diag-suppress", "186,128"]
 SOURCES = ["ntt_v4_inst_d.cu", "ntt_v4_inst_c.cu", "ntt_v4_inst_b.cu", "ntt_v4_inst_a.cu", "ntt_inst_a.cu", "ntt_inst_b.cu", "ntt_inst_c.cu", "ntt_inst_d.cu", "ntt_dispatch.cu", "ntt_engine.cu",
            "fri_fold.cu", "merkle.cu", "c_abi.cu"]
 SO = os.path.join(HERE, "libntt_cuda.so")

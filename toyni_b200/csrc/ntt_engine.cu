@@ -24,10 +24,13 @@ __device__ __forceinline__ uint32_t monty_pow_dev(uint32_t g_m, uint32_t e) {
     return r;
 }
 
-// out[i] = g^i * scale, Montgomery form
-__global__ void gen_pow_kernel(uint32_t* out, uint32_t count, uint32_t g_m, uint32_t scale_m) {
+// out[i] = Shoup pair of g^i * scale (plain form)
+__global__ void gen_pow_kernel(uint2* out, uint32_t count, uint32_t g_m, uint32_t scale) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = monty_mul(monty_pow_dev(g_m, i), scale_m);
+    if (i < count) {
+        uint32_t w = monty_mul(monty_pow_dev(g_m, i), scale);  // (g^i R) * scale / R
+        out[i] = make_uint2(w, shoup_companion(w));
+    }
 }
 
 // out[i] = (w, floor(w 2^32 / p)) with w = g^i, plain form
@@ -41,8 +44,8 @@ __global__ void gen_shoup_kernel(uint2* out, uint32_t count, uint32_t g_m) {
 
 // ------------------------------------------------------------------ per-device state
 struct PowTab {
-    uint32_t* lo = nullptr;
-    uint32_t* hi = nullptr;
+    uint2* lo = nullptr;
+    uint2* hi = nullptr;
     uint32_t lo_bits = 0;
 };
 
@@ -100,10 +103,10 @@ static int pow_table_get(DeviceState& st, uint32_t g, int log_total, uint32_t sc
         PowTab t;
         t.lo_bits = (uint32_t)((log_total + 1) / 2);
         uint32_t n_lo = 1u << t.lo_bits, n_hi = 1u << (log_total - (int)t.lo_bits);
-        BB_CK(cudaMalloc(&t.lo, sizeof(uint32_t) * n_lo));
-        BB_CK(cudaMalloc(&t.hi, sizeof(uint32_t) * n_hi));
-        gen_pow_kernel<<<(n_lo + 255) / 256, 256>>>(t.lo, n_lo, to_monty(g), to_monty(scale));
-        gen_pow_kernel<<<(n_hi + 255) / 256, 256>>>(t.hi, n_hi, to_monty(bb::pow(g, n_lo)), R_MOD_P);
+        BB_CK(cudaMalloc(&t.lo, sizeof(uint2) * n_lo));
+        BB_CK(cudaMalloc(&t.hi, sizeof(uint2) * n_hi));
+        gen_pow_kernel<<<(n_lo + 255) / 256, 256>>>(t.lo, n_lo, to_monty(g), scale);
+        gen_pow_kernel<<<(n_hi + 255) / 256, 256>>>(t.hi, n_hi, to_monty(bb::pow(g, n_lo)), 1u);
         BB_CK(cudaGetLastError());
         // generated on the legacy default stream: make them visible to any (possibly non-blocking) stream
         BB_CK(cudaDeviceSynchronize());
@@ -192,20 +195,25 @@ static NttPlan plan_locked(int log_n, int log_inner, size_t batch) {
     if (it != g_plan_override.end()) return it->second;
     NttPlan pl;
     memset(&pl, 0, sizeof pl);
-    if (log_n <= MAX_LR) {
+    // Measured on B200 (tools/plan_sweep.py): passes of about 2^8 rows x 16 columns (16 KB tiles, double buffered,
+    // 7 CTAs per SM) beat fewer, larger passes — the kernels are instruction-bound, not DRAM-bound, and the
+    // intermediate arrays of a <= 2^24 transform mostly stay in the 126 MB L2.
+    if (log_n <= 8 && log_inner == 0) {
+        // short plain vectors: one pass of the scalar kernel, the vectors of the batch are the tile columns
         pl.npass = 1;
         pl.lr[0] = log_n;
-        if (log_inner > 0) {
-            pl.lc[0] = pick_lc(log_n, log_inner);
-        } else {
-            // columns are the vectors of the batch: aim for ~4096-element tiles
-            int want = MAX_LR - log_n;
-            int lb = ceil_log2(batch);
-            pl.lc[0] = pick_lc(log_n, want < lb ? want : lb);
-        }
+        int want = MAX_LR - log_n;
+        int lb = ceil_log2(batch);
+        pl.lc[0] = pick_lc(log_n, want < lb ? want : lb);
         return pl;
     }
-    if (log_n <= 2 * MAX_LR) {
+    if (log_n <= 6 || (log_inner > 0 && log_n <= 8)) {
+        pl.npass = 1;
+        pl.lr[0] = log_n;
+        pl.lc[0] = pick_lc(log_n, log_inner > 0 ? log_inner : 0);
+        return pl;
+    }
+    if (log_n <= 16) {
         pl.npass = 2;
         pl.lr[0] = (log_n + 1) / 2;
         pl.lr[1] = log_n - pl.lr[0];
@@ -216,15 +224,13 @@ static NttPlan plan_locked(int log_n, int log_inner, size_t batch) {
         pl.lr[2] = log_n - pl.lr[0] - pl.lr[1];
     }
     for (int i = 0; i < pl.npass; i++) {
-        // tiles of about 8192 elements keep several CTAs resident per SM; never below 8 columns (32-byte segments)
-        int want = 13 - pl.lr[i];
-        if (want < 3) want = 3;
+        int ncols_log = log_n - pl.lr[i] + log_inner;
+        int want = 4;  // 16 columns = 64-byte row segments
+        if (want > ncols_log) want = ncols_log;
         pl.lc[i] = pick_lc(pl.lr[i], want);
     }
     return pl;
 }
-
-void engine_force_scalar(bool on) { g_force_scalar = on; }
 
 NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -334,7 +340,6 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
         p.in = src;
         p.out = dst;
         p.tw = st->tw[inv];
-        p.log_tw = LOG_TW;
         memcpy(p.tw16, st->tw16[inv], sizeof p.tw16);
         p.log_inner = (uint32_t)d.log_inner;
         p.n_in_limit = first ? (unsigned long long)d.n_in * inner : ~0ull;
@@ -369,6 +374,7 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
             p.epi_mode = EPI_TWIDDLE;
             p.epi = first ? tw_first : tw_rest;
             p.epi_shift = (uint32_t)log_p;
+            p.epi_unscale = (first && inv && !coset) ? to_monty((uint32_t)(n % P)) : R_MOD_P;
         } else if (coset && inv) {
             p.epi_mode = EPI_OUTIDX;
             p.epi = coset_tab;

@@ -12,7 +12,6 @@ namespace bb {
 
 constexpr int MAX_LOG_N = 27;  // two-adicity of BabyBear, src/babybear.rs:119
 constexpr int MAX_LR = 12;     // largest in-tile transform
-constexpr int LOG_TW = 12;     // master Shoup table covers omega_4096
 
 struct NttPlan {
     int npass;

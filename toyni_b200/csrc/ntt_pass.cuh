@@ -23,13 +23,15 @@
 
 namespace bb {
 
+constexpr int LOG_TW = 12;  // the master Shoup twiddle table covers omega_4096 (largest in-tile transform)
+
 enum : uint32_t { PRO_NONE = 0, PRO_INIDX = 1 };
 enum : uint32_t { EPI_NONE = 0, EPI_TWIDDLE = 1, EPI_OUTIDX = 2, EPI_CONST = 3 };
 
-// g^t = hi[t >> lo_bits] * lo[t & mask]; both tables hold Montgomery-form values
+// g^t = hi[t >> lo_bits] * lo[t & mask]; entries are Shoup pairs (w, floor(w 2^32 / p)) of plain values
 struct PowTable {
-    const uint32_t* lo;
-    const uint32_t* hi;
+    const uint2* lo;
+    const uint2* hi;
     uint32_t lo_bits;
 };
 
@@ -43,13 +45,13 @@ struct PassParams {
     uint32_t ncols;                                        // number of columns (u32 units, incl. interleave)
     uint32_t log_pfull;                                    // log2(pfull)
     uint32_t log_inner;                                    // log2(interleave factor)
-    const uint2* tw;                                       // Shoup table: (w, w') of omega_T^i, i < T/2
-    uint32_t log_tw;                                       // log2 T
+    const uint2* tw;                                       // Shoup table: (w, w') of omega_4096^i, i < 2048
     uint2 tw16[8];                                         // (w, w') of omega_16^i (i<8) in this direction
     uint32_t transposed;                                   // 1: rows contiguous in memory (batch of vectors)
     uint32_t pro_mode, epi_mode;
     PowTable pro, epi;
     uint32_t epi_const;  // Montgomery-form constant for EPI_CONST
+    uint32_t epi_unscale;  // Montgomery form of the inverse of the constant factor folded into epi.lo (R mod p if none)
     uint32_t epi_shift;  // EPI_TWIDDLE exponent = (j*e) << epi_shift
 };
 
@@ -67,17 +69,26 @@ __host__ __device__ constexpr int pass_threads(int LR, int LC) {
 }
 __host__ __device__ constexpr size_t pass_smem_bytes(int LR, int LC) { return (size_t)col_pitch(LR, LC) * (1u << LC) * 4u; }
 
+// a + b on the ALU pipe: written as min(a + b, UINT_MAX) so that ptxas emits VIADDMNMX instead of turning the add
+// into IMAD.IADD — the FMA-heavy pipe is the bottleneck of a butterfly (IMAD.HI costs 2.7 issue slots there)
+BB_D uint32_t add_alu(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__) && !defined(BB_PLAIN_ADD)
+    return __viaddmin_u32(a, b, 0xFFFFFFFFu);
+#else
+    return a + b;
+#endif
+}
 BB_D void bfly(uint32_t& u, uint32_t& x, uint2 w) {
     uint32_t v = shoup_mul_lazy(x, w.x, w.y);
     v = min(v, v - P);
     uint32_t uu = min(u, u - P);
-    u = uu + v;
+    u = add_alu(uu, v);
     x = uu - v + P;
 }
 BB_D void bfly_one(uint32_t& u, uint32_t& x) {  // twiddle == 1
     uint32_t v = min(x, x - P);
     uint32_t uu = min(u, u - P);
-    u = uu + v;
+    u = add_alu(uu, v);
     x = uu - v + P;
 }
 
@@ -94,7 +105,7 @@ BB_D void dit_round(uint32_t* __restrict__ sm, const PassParams& p) {
     const int tid = threadIdx.x;
     const int rg0 = tid % RGT, c0 = tid / RGT;
     const uint2* __restrict__ tw = p.tw;
-    const uint32_t log_tw = p.log_tw;
+    constexpr uint32_t log_tw = LOG_TW;
 #pragma unroll 1
     for (int rg = rg0; rg < RG; rg += RGT) {
         const int b = rg & (S - 1), blk = rg >> S_LOG;
@@ -139,10 +150,20 @@ BB_D void dit_round(uint32_t* __restrict__ sm, const PassParams& p) {
     }
 }
 
+// Montgomery form of g^e (for a factor shared by several values)
 BB_D uint32_t pow_lookup(const PowTable& t, uint32_t e) {
-    uint32_t lo = __ldg(&t.lo[e & ((1u << t.lo_bits) - 1u)]);
-    uint32_t hi = __ldg(&t.hi[e >> t.lo_bits]);
-    return monty_mul(hi, lo);  // Montgomery form of g^e
+    const uint2 lo = __ldg(&t.lo[e & ((1u << t.lo_bits) - 1u)]);
+    const uint2 hi = __ldg(&t.hi[e >> t.lo_bits]);
+    const uint32_t w = shoup_mul_lazy(lo.x, hi.x, hi.y);  // lo*hi in [0,2p)
+    return monty_mul(w, R2_MOD_P);                         // canonical, times R
+}
+// v * g^e, canonical, for any 32-bit v: two Shoup multiplications, no product twiddle formed
+BB_D uint32_t pow_apply(const PowTable& t, uint32_t e, uint32_t v) {
+    const uint2 lo = __ldg(&t.lo[e & ((1u << t.lo_bits) - 1u)]);
+    const uint2 hi = __ldg(&t.hi[e >> t.lo_bits]);
+    v = shoup_mul_lazy(v, lo.x, lo.y);
+    v = shoup_mul_lazy(v, hi.x, hi.y);
+    return min(v, v - P);
 }
 
 template <int LR, int LC>
@@ -178,7 +199,7 @@ __global__ void __launch_bounds__(pass_threads(LR, LC)) ntt_pass_kernel(const Pa
         uint32_t v = 0;
         if (col < p.ncols && lidx < p.n_in_limit) {
             v = in[(size_t)d * p.in_row_stride + (size_t)col * p.in_col_stride];
-            if (p.pro_mode == PRO_INIDX) v = monty_mul(v, pow_lookup(p.pro, (uint32_t)(lidx >> p.log_inner)));
+            if (p.pro_mode == PRO_INIDX) v = pow_apply(p.pro, (uint32_t)(lidx >> p.log_inner), v);
         }
         sm[c * PITCH + r + (r >> 4)] = v;
     }
@@ -211,10 +232,10 @@ __global__ void __launch_bounds__(pass_threads(LR, LC)) ntt_pass_kernel(const Pa
         const uint32_t j = col >> p.log_pfull, low = col & pfull_mask;
         switch (p.epi_mode) {
             case EPI_TWIDDLE:
-                v = monty_mul(v, pow_lookup(p.epi, (j * e) << p.epi_shift));
+                v = pow_apply(p.epi, (j * e) << p.epi_shift, v);
                 break;
             case EPI_OUTIDX:
-                v = monty_mul(v, pow_lookup(p.epi, ((e << p.log_pfull) + low) >> p.log_inner));
+                v = pow_apply(p.epi, ((e << p.log_pfull) + low) >> p.log_inner, v);
                 break;
             case EPI_CONST:
                 v = monty_mul(v, p.epi_const);

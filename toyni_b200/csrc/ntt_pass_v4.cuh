@@ -5,7 +5,8 @@
 //   * every radix-16 round moves data with LDS.128 / STS.128 and the four columns of a chunk share their twiddles,
 //   * shared -> global is STG.128 (row-granular passes) or four coalesced STG.32 (the transposing first pass).
 // Bank conflicts are removed by an XOR swizzle on the chunk index that is GF(2)-linear in (row, chunk), so the
-// address of row (row0 | k*S) is base ^ constant_k.
+// address of row (row0 | k*S) is base ^ constant_k; all loops are fully unrolled so those constants, the
+// bit-reversed row numbers and the global strides fold at compile time.
 #pragma once
 #include "ntt_pass.cuh"
 
@@ -19,16 +20,30 @@ struct V4 {
     static constexpr int G1 = LR < 4 ? LR : 4;
     static constexpr int G2 = (LR - G1) < 4 ? (LR - G1) : 4;
     static constexpr int G3 = LR - G1 - G2;
-    static constexpr int ITEMS = (R >> G1) * CV;  // work items of the first round
+#ifndef BB_VW
+#define BB_VW 2
+#endif
+    // a work item of a round is 16 rows x VW adjacent columns; VW = 2 halves the register footprint of VW = 4
+    // (32 instead of 64 live values), which doubles the warps per SM at the same tile size
+    static constexpr int VW = ((R >> G1) * (C / BB_VW) <= 512) ? BB_VW : 4;
+    static constexpr int LVW = (VW == 4) ? 2 : 1;
+    static constexpr int ITEMS = (R >> G1) * (C / VW);  // work items of the first round
     static constexpr int NT = ITEMS < 32 ? 32 : (ITEMS > 512 ? 512 : ITEMS);
+    static constexpr int CHUNKS = R * CV;
+    static constexpr int RS = NT >> LCV;  // rows covered by one sweep of the CTA over chunks (when > 0)
     static constexpr size_t SMEM = (size_t)R * C * 4;
 
-    // physical 16-byte chunk index of (row, cv)
+    // physical 16-byte chunk index of (row, cv); GF(2)-linear in its arguments
     __host__ __device__ static constexpr uint32_t chunk(uint32_t row, uint32_t cv) {
         constexpr uint32_t qm = (1u << Q) - 1u;
         uint32_t rin = (row & qm) ^ ((row >> 4) & qm);
         uint32_t cvv = cv ^ ((row >> Q) & (CV - 1u));
         return ((row >> Q) << 3) | (rin << LCV) | cvv;
+    }
+    __host__ __device__ static constexpr uint32_t brev(uint32_t r) {  // LR-bit reversal
+        uint32_t x = 0;
+        for (int i = 0; i < LR; i++) x |= ((r >> i) & 1u) << (LR - 1 - i);
+        return x;
     }
 };
 
@@ -45,42 +60,79 @@ BB_D void bfly4_one(uint4& u, uint4& x) {
     bfly_one(u.w, x.w);
 }
 
+template <int VW>
+struct Vec;
+template <>
+struct Vec<4> {
+    typedef uint4 type;
+};
+template <>
+struct Vec<2> {
+    typedef uint2 type;
+};
+
 template <int LR, int LC, int S_LOG, int G_LOG>
 BB_D void dit_round_v4(uint4* __restrict__ sm, const PassParams& p) {
     using T = V4<LR, LC>;
-    constexpr int R = T::R, CV = T::CV, NT = T::NT, S = 1 << S_LOG, G = 1 << G_LOG;
-    constexpr int ITEMS = (R / G) * CV;
-    const uint2* __restrict__ tw = p.tw;
-    const uint32_t log_tw = p.log_tw;
+    constexpr int R = T::R, NT = T::NT, S = 1 << S_LOG, G = 1 << G_LOG, VW = T::VW;
+    constexpr int CW = T::C / VW;  // items per row
+    constexpr int ITEMS = (R / G) * CW;
+    typedef typename Vec<VW>::type vec_t;
+    const char* __restrict__ twb = reinterpret_cast<const char*>(p.tw);
+    vec_t* __restrict__ smw = reinterpret_cast<vec_t*>(sm);
 #pragma unroll 1
     for (int it = threadIdx.x; it < ITEMS; it += NT) {
-        const uint32_t cv = it & (CV - 1);
-        const uint32_t rg = it >> T::LCV;
+        const uint32_t cw = it & (CW - 1);
+        const uint32_t cv = (VW == 4) ? cw : (cw >> 1), sub = (VW == 4) ? 0u : (cw & 1u);
+        const uint32_t rg = it / CW;
         const uint32_t b = rg & (S - 1), blk = rg >> S_LOG;
         const uint32_t row0 = blk * (G * S) + b;
-        const uint32_t base = T::chunk(row0, cv);
-        uint4 x[G];
+        const uint32_t base = (VW == 4) ? T::chunk(row0, cv) : ((T::chunk(row0, cv) << 1) | sub);
+        uint32_t x[G][VW];
 #pragma unroll
-        for (int k = 0; k < G; k++) x[k] = sm[base ^ T::chunk((uint32_t)k << S_LOG, 0)];
+        for (int k = 0; k < G; k++) {
+            const vec_t v = smw[base ^ (T::chunk((uint32_t)k << S_LOG, 0) << (VW == 4 ? 0 : 1))];
+            if constexpr (VW == 4) {
+                x[k][0] = v.x; x[k][1] = v.y; x[k][2] = v.z; x[k][3] = v.w;
+            } else {
+                x[k][0] = v.x; x[k][1] = v.y;
+            }
+        }
 #pragma unroll
         for (int t = 0; t < G_LOG; t++) {
+            // stage t twiddle kp is omega_4096^((b + kp*S) << sh): one base address per stage, kp folds into the offset
+            const int sh = (S_LOG == 0) ? 0 : (LOG_TW - (S_LOG + t + 1));
+            const char* tws = twb + ((size_t)(b << sh) << 3);
 #pragma unroll
             for (int k = 0; k < G; k++) {
                 if (k & (1 << t)) continue;
                 const int kp = k & ((1 << t) - 1);
                 if (S_LOG == 0) {
-                    if (kp == 0)
-                        bfly4_one(x[k], x[k + (1 << t)]);
-                    else
-                        bfly4(x[k], x[k + (1 << t)], p.tw16[kp << (3 - t)]);
+                    if (kp == 0) {
+#pragma unroll
+                        for (int c = 0; c < VW; c++) bfly_one(x[k][c], x[k + (1 << t)][c]);
+                    } else {
+                        const uint2 w = p.tw16[kp << (3 - t)];
+#pragma unroll
+                        for (int c = 0; c < VW; c++) bfly(x[k][c], x[k + (1 << t)][c], w);
+                    }
                 } else {
-                    const uint32_t idx = (b + (uint32_t)kp * S) << (log_tw - (S_LOG + t + 1));
-                    bfly4(x[k], x[k + (1 << t)], __ldg(&tw[idx]));
+                    const uint2 w = __ldg(reinterpret_cast<const uint2*>(tws + ((size_t)((kp * S) << sh) << 3)));
+#pragma unroll
+                    for (int c = 0; c < VW; c++) bfly(x[k][c], x[k + (1 << t)][c], w);
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < G; k++) sm[base ^ T::chunk((uint32_t)k << S_LOG, 0)] = x[k];
+        for (int k = 0; k < G; k++) {
+            vec_t v;
+            if constexpr (VW == 4) {
+                v.x = x[k][0]; v.y = x[k][1]; v.z = x[k][2]; v.w = x[k][3];
+            } else {
+                v.x = x[k][0]; v.y = x[k][1];
+            }
+            smw[base ^ (T::chunk((uint32_t)k << S_LOG, 0) << (VW == 4 ? 0 : 1))] = v;
+        }
     }
 }
 
@@ -89,22 +141,178 @@ BB_D uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_sha
 BB_D uint4 mul4(uint4 v, uint32_t w_m) {
     return make_uint4(monty_mul(v.x, w_m), monty_mul(v.y, w_m), monty_mul(v.z, w_m), monty_mul(v.w, w_m));
 }
+BB_D uint4 canon4(uint4 v) { return make_uint4(min(v.x, v.x - P), min(v.y, v.y - P), min(v.z, v.z - P), min(v.w, v.w - P)); }
 
+// ---- epilogue + store for passes whose chunks stay whole in the output (log_pfull >= 2)
+template <int LR, int LC, uint32_t EPI>
+BB_D void store_rows_v4(const uint4* __restrict__ smv, uint32_t* __restrict__ out, const PassParams& p, uint32_t col0) {
+    using T = V4<LR, LC>;
+    constexpr int R = T::R, CV = T::CV, LCV = T::LCV, NT = T::NT;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t log_pfull = p.log_pfull;
+    if (log_pfull >= (uint32_t)LC) {
+        // the whole tile shares j: row e is one contiguous segment of C values
+        const uint32_t j = col0 >> log_pfull, low = (col0 & ((1u << log_pfull) - 1u));
+        if constexpr (T::RS > 0 && (T::CHUNKS % NT) == 0) {
+            const uint32_t cv = tid & (CV - 1), e0 = tid >> LCV;
+            const uint32_t sbase = T::chunk(e0, cv);
+            uint32_t* o = out + ((((size_t)j << LR) + e0) << log_pfull) + low + 4u * cv;
+            const size_t step = (size_t)T::RS << log_pfull;
+            uint32_t tw = 0, twstep = 0;  // running inter-pass twiddle g^e, g = omega^(j << shift), Montgomery form
+            if (EPI == EPI_TWIDDLE) {
+                tw = pow_lookup(p.epi, (j * e0) << p.epi_shift);
+                // g^RS; the table may carry a constant factor (n^-1 of an inverse transform), taken out again here
+                twstep = monty_mul(pow_lookup(p.epi, (j * (uint32_t)T::RS) << p.epi_shift), p.epi_unscale);
+            }
+#pragma unroll
+            for (int it = 0; it < T::CHUNKS / NT; it++) {
+                uint4 v = smv[sbase ^ T::chunk((uint32_t)(it * T::RS), 0)];
+                if (EPI == EPI_TWIDDLE) {
+                    v = mul4(v, tw);
+                    tw = monty_mul(tw, twstep);
+                } else if (EPI == EPI_OUTIDX) {
+                    const uint32_t k = (((uint32_t)(it * T::RS) + e0) << log_pfull) + low + 4u * cv;
+                    if (p.log_inner >= 2) {
+                        v = mul4(v, pow_lookup(p.epi, k >> p.log_inner));
+                    } else {
+                        v.x = pow_apply(p.epi, (k + 0) >> p.log_inner, v.x);
+                        v.y = pow_apply(p.epi, (k + 1) >> p.log_inner, v.y);
+                        v.z = pow_apply(p.epi, (k + 2) >> p.log_inner, v.z);
+                        v.w = pow_apply(p.epi, (k + 3) >> p.log_inner, v.w);
+                    }
+                } else if (EPI == EPI_CONST) {
+                    v = mul4(v, p.epi_const);
+                } else {
+                    v = canon4(v);
+                }
+                *reinterpret_cast<uint4*>(o + (size_t)it * step) = v;
+            }
+            return;
+        }
+    }
+    // general form: runs of min(C, pfull) columns are contiguous in the output
+    const uint32_t pfull_mask = (1u << log_pfull) - 1u;
+    const uint32_t log_clv = (log_pfull < (uint32_t)LC ? log_pfull : (uint32_t)LC) - 2;
+    const uint32_t j0 = col0 >> log_pfull, low0 = col0 & pfull_mask;
+#pragma unroll 2
+    for (int i = tid; i < R * CV; i += NT) {
+        const uint32_t lv = i & ((1u << log_clv) - 1u);
+        const uint32_t e = (i >> log_clv) & (R - 1);
+        const uint32_t jj = i >> (log_clv + LR);
+        const uint32_t cv = (jj << log_clv) + lv;
+        uint4 v = smv[T::chunk(e, cv)];
+        const uint32_t j = j0 + jj, low = low0 + 4u * lv;
+        if (EPI == EPI_TWIDDLE) {
+            v = mul4(v, pow_lookup(p.epi, (j * e) << p.epi_shift));
+        } else if (EPI == EPI_OUTIDX) {
+            const uint32_t k = (e << log_pfull) + low;
+            if (p.log_inner >= 2) {
+                v = mul4(v, pow_lookup(p.epi, k >> p.log_inner));
+            } else {
+                v.x = pow_apply(p.epi, (k + 0) >> p.log_inner, v.x);
+                v.y = pow_apply(p.epi, (k + 1) >> p.log_inner, v.y);
+                v.z = pow_apply(p.epi, (k + 2) >> p.log_inner, v.z);
+                v.w = pow_apply(p.epi, (k + 3) >> p.log_inner, v.w);
+            }
+        } else if (EPI == EPI_CONST) {
+            v = mul4(v, p.epi_const);
+        } else {
+            v = canon4(v);
+        }
+        *reinterpret_cast<uint4*>(out + ((((size_t)j << LR) + e) << log_pfull) + low) = v;
+    }
+}
+
+// ---- epilogue + store for the first pass of a plain vector (pfull == 1): column col becomes the contiguous run
+//      out[col*R + e]; lanes walk e, so each of the four scalar stores of a chunk is coalesced.  The inter-pass
+//      twiddle w^(col*e) is generated on chip: for a fixed row e it is a geometric sequence in col, so a thread
+//      that owns row e for all C columns needs two table lookups (w^(col0*e), w^e) and one multiply per value.
+template <int LR, int LC, uint32_t EPI>
+BB_D void store_cols_v4(const uint4* __restrict__ smv, uint32_t* __restrict__ out, const PassParams& p, uint32_t col0) {
+    using T = V4<LR, LC>;
+    constexpr int R = T::R, CV = T::CV, NT = T::NT;
+    const uint32_t tid = threadIdx.x;
+    if constexpr (NT <= R && (R % NT) == 0) {
+#pragma unroll 1
+        for (uint32_t e = tid; e < (uint32_t)R; e += NT) {
+            uint32_t tw = 0, g = 0;
+            if (EPI == EPI_TWIDDLE) {
+                tw = pow_lookup(p.epi, (col0 * e) << p.epi_shift);                       // carries the table's constant factor
+                g = monty_mul(pow_lookup(p.epi, e << p.epi_shift), p.epi_unscale);     // w^e without it
+            }
+            uint32_t* o = out + ((size_t)col0 << LR) + e;
+#pragma unroll
+            for (int cv = 0; cv < CV; cv++) {
+                uint4 v = smv[T::chunk(e, cv)];
+                if (EPI == EPI_TWIDDLE) {
+                    v.x = monty_mul(v.x, tw); tw = monty_mul(tw, g);
+                    v.y = monty_mul(v.y, tw); tw = monty_mul(tw, g);
+                    v.z = monty_mul(v.z, tw); tw = monty_mul(tw, g);
+                    v.w = monty_mul(v.w, tw); tw = monty_mul(tw, g);
+                } else if (EPI == EPI_CONST) {
+                    v = mul4(v, p.epi_const);
+                } else {
+                    v = canon4(v);
+                }
+                o[(size_t)(4 * cv + 0) << LR] = v.x;
+                o[(size_t)(4 * cv + 1) << LR] = v.y;
+                o[(size_t)(4 * cv + 2) << LR] = v.z;
+                o[(size_t)(4 * cv + 3) << LR] = v.w;
+            }
+        }
+        return;
+    }
+#pragma unroll 4
+    for (int i = tid; i < R * CV; i += NT) {
+        const uint32_t e = i & (R - 1), cv = i >> LR;
+        uint4 v = smv[T::chunk(e, cv)];
+        const uint32_t col = col0 + 4u * cv;
+        if (EPI == EPI_TWIDDLE) {
+            const uint32_t t0 = (col * e) << p.epi_shift, dt = e << p.epi_shift;
+            v.x = pow_apply(p.epi, t0, v.x);
+            v.y = pow_apply(p.epi, t0 + dt, v.y);
+            v.z = pow_apply(p.epi, t0 + 2 * dt, v.z);
+            v.w = pow_apply(p.epi, t0 + 3 * dt, v.w);
+        } else if (EPI == EPI_CONST) {
+            v = mul4(v, p.epi_const);
+        } else {
+            v = canon4(v);
+        }
+        uint32_t* o = out + ((size_t)col << LR) + e;
+        o[0] = v.x;
+        o[(size_t)1 << LR] = v.y;
+        o[(size_t)2 << LR] = v.z;
+        o[(size_t)3 << LR] = v.w;
+    }
+}
+
+// global -> shared for one tile (asynchronous; the caller commits / waits)
 template <int LR, int LC>
-__global__ void __launch_bounds__(V4<LR, LC>::NT) ntt_pass_v4_kernel(const PassParams p) {
+BB_D void load_tile_v4(uint4* __restrict__ buf, const uint32_t* __restrict__ in, const PassParams& p, uint32_t col0) {
     using T = V4<LR, LC>;
     constexpr int R = T::R, C = T::C, CV = T::CV, LCV = T::LCV, NT = T::NT;
-    extern __shared__ uint4 smv[];
-
-    const int tid = threadIdx.x;
-    const uint32_t col0 = blockIdx.x * C;
-    const uint32_t* __restrict__ in = p.in + (size_t)blockIdx.y * p.in_batch_stride;
-    uint32_t* __restrict__ out = p.out + (size_t)blockIdx.y * p.out_batch_stride;
+    const uint32_t tid = threadIdx.x;
     const uint32_t ncols = p.ncols;
-
-    // ---- load: one 16-byte cp.async per chunk, row d of the tile lands at row bitrev(d); bytes past the
-    //      zero-padding limit are zero-filled by the copy engine
-#pragma unroll 4
+    const bool full = (unsigned long long)(R - 1) * ncols + col0 + C <= p.n_in_limit;  // no zero padding in this tile
+    if constexpr (T::RS > 0 && (T::CHUNKS % NT) == 0) {
+        if (full) {
+            const uint32_t cv = tid & (CV - 1), r0 = tid >> LCV;
+            const uint32_t sm0 = smem_u32(buf), cbase = T::chunk(r0, cv);
+            const uint32_t d0 = (LR == 0) ? 0u : (__brev(r0) >> (32 - LR));
+            const uint32_t* src0 = in + (size_t)d0 * ncols + col0 + 4u * cv;
+#pragma unroll
+            for (int it = 0; it < T::CHUNKS / NT; it++) {
+                // row r0 | it*RS (disjoint bits): the swizzle and the bit reversal split into thread part ^ constant
+                const uint32_t* src = src0 + (size_t)T::brev((uint32_t)(it * T::RS)) * ncols;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sm0 + ((cbase ^ T::chunk((uint32_t)(it * T::RS), 0)) << 4)),
+                             "l"(src)
+                             : "memory");
+            }
+            return;
+        }
+    }
+    // zero-padded input (the coset LDE reads n_coeffs << size values): bytes past the limit are zero-filled
+#pragma unroll 1
     for (int i = tid; i < R * CV; i += NT) {
         const uint32_t cv = i & (CV - 1), r = i >> LCV;
         const uint32_t d = (LR == 0) ? 0u : (__brev(r) >> (32 - LR));
@@ -112,125 +320,121 @@ __global__ void __launch_bounds__(V4<LR, LC>::NT) ntt_pass_v4_kernel(const PassP
         const unsigned long long remw = p.n_in_limit > lidx ? p.n_in_limit - lidx : 0ull;  // valid words from here
         const uint32_t bytes = remw >= 4ull ? 16u : (uint32_t)remw * 4u;
         const uint32_t* src = in + (bytes ? lidx : 0ull);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(&smv[T::chunk(r, cv)])), "l"(src), "r"(bytes)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(&buf[T::chunk(r, cv)])), "l"(src), "r"(bytes)
                      : "memory");
     }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-    __syncthreads();
+}
 
-    if (p.pro_mode == PRO_INIDX) {  // coset shift of the (few) real input rows: x[i] *= s^i
-        const uint32_t rows_in = (uint32_t)((p.n_in_limit + ncols - 1) / ncols);  // rows that hold any input
+// Persistent CTAs walk the tiles (tile = batch index * tiles_per_vector + column tile).  With DB the next tile's
+// cp.async traffic is in flight while the current one is transformed, so the DRAM latency of the load is hidden
+// even at 2-4 warps per CTA.
+template <int LR, int LC, bool DB>
+__global__ void __launch_bounds__(V4<LR, LC>::NT) ntt_pass_v4_kernel(const PassParams p, uint32_t tiles_x, uint32_t total_tiles) {
+    using T = V4<LR, LC>;
+    constexpr int R = T::R, C = T::C, CV = T::CV, LCV = T::LCV, NT = T::NT;
+    extern __shared__ uint4 smv_all[];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t ncols = p.ncols;
+    uint32_t tile = blockIdx.x;
+    if (tile >= total_tiles) return;
+    if (DB) {
+        const uint32_t bz = tile / tiles_x, tx = tile - bz * tiles_x;
+        load_tile_v4<LR, LC>(smv_all, p.in + (size_t)bz * p.in_batch_stride, p, tx * C);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    for (uint32_t iter = 0; tile < total_tiles; tile += gridDim.x, iter++) {
+        const uint32_t bz = tile / tiles_x, tx = tile - bz * tiles_x;
+        const uint32_t col0 = tx * C;
+        uint32_t* __restrict__ out = p.out + (size_t)bz * p.out_batch_stride;
+        uint4* smv = smv_all + ((DB && (iter & 1)) ? T::CHUNKS : 0);
+        if (DB) {
+            const uint32_t nt = tile + gridDim.x;
+            if (nt < total_tiles) {
+                const uint32_t nbz = nt / tiles_x, ntx = nt - nbz * tiles_x;
+                load_tile_v4<LR, LC>(smv_all + ((iter & 1) ? 0 : T::CHUNKS), p.in + (size_t)nbz * p.in_batch_stride, p, ntx * C);
+            }
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;\n" ::: "memory");
+        } else {
+            load_tile_v4<LR, LC>(smv, p.in + (size_t)bz * p.in_batch_stride, p, col0);
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+        }
+        __syncthreads();
+
+        if (p.pro_mode == PRO_INIDX) {  // coset shift of the (few) real input rows: x[i] *= s^i
+            const uint32_t rows_in = (uint32_t)((p.n_in_limit + ncols - 1) / ncols);  // rows that hold any input
 #pragma unroll 1
-        for (uint32_t i = tid; i < rows_in * CV && i < (uint32_t)(R * CV); i += NT) {
-            const uint32_t cv = i & (CV - 1), d = i >> LCV;
-            const uint32_t r = (LR == 0) ? 0u : (__brev(d) >> (32 - LR));
-            const uint32_t lidx = d * ncols + col0 + 4u * cv;
-            uint4 v = smv[T::chunk(r, cv)];
-            if (p.log_inner >= 2) {
-                v = mul4(v, pow_lookup(p.pro, lidx >> p.log_inner));
-            } else {
-                v.x = monty_mul(v.x, pow_lookup(p.pro, (lidx + 0) >> p.log_inner));
-                v.y = monty_mul(v.y, pow_lookup(p.pro, (lidx + 1) >> p.log_inner));
-                v.z = monty_mul(v.z, pow_lookup(p.pro, (lidx + 2) >> p.log_inner));
-                v.w = monty_mul(v.w, pow_lookup(p.pro, (lidx + 3) >> p.log_inner));
-            }
-            smv[T::chunk(r, cv)] = v;
-        }
-        __syncthreads();
-    }
-
-    // ---- radix-16 DIT rounds, strides 1, 16, 256
-    if constexpr (T::G1 > 0) dit_round_v4<LR, LC, 0, T::G1>(smv, p);
-    if constexpr (T::G2 > 0) {
-        __syncthreads();
-        dit_round_v4<LR, LC, 4, T::G2>(smv, p);
-    }
-    if constexpr (T::G3 > 0) {
-        __syncthreads();
-        dit_round_v4<LR, LC, 8, T::G3>(smv, p);
-    }
-    __syncthreads();
-
-    // ---- epilogue + store
-    const uint32_t log_pfull = p.log_pfull;
-    const uint32_t pfull_mask = (1u << log_pfull) - 1u;
-    if (log_pfull >= 2) {
-        // chunks stay whole in the output: the four values of a chunk share j (and the inter-pass twiddle)
-        const uint32_t log_clv = (log_pfull < (uint32_t)LC ? log_pfull : (uint32_t)LC) - 2;  // chunks per contiguous run
-        const uint32_t j0 = col0 >> log_pfull, low0 = col0 & pfull_mask;
-#pragma unroll 2
-        for (int i = tid; i < R * CV; i += NT) {
-            const uint32_t lv = i & ((1u << log_clv) - 1u);
-            const uint32_t e = (i >> log_clv) & (R - 1);
-            const uint32_t jj = i >> (log_clv + LR);
-            const uint32_t cv = (jj << log_clv) + lv;
-            uint4 v = smv[T::chunk(e, cv)];
-            const uint32_t j = j0 + jj, low = low0 + 4u * lv;
-            switch (p.epi_mode) {
-                case EPI_TWIDDLE:
-                    v = mul4(v, pow_lookup(p.epi, (j * e) << p.epi_shift));
-                    break;
-                case EPI_OUTIDX: {
-                    const uint32_t k = (e << log_pfull) + low;
-                    if (p.log_inner >= 2) {
-                        v = mul4(v, pow_lookup(p.epi, k >> p.log_inner));
-                    } else {
-                        v.x = monty_mul(v.x, pow_lookup(p.epi, (k + 0) >> p.log_inner));
-                        v.y = monty_mul(v.y, pow_lookup(p.epi, (k + 1) >> p.log_inner));
-                        v.z = monty_mul(v.z, pow_lookup(p.epi, (k + 2) >> p.log_inner));
-                        v.w = monty_mul(v.w, pow_lookup(p.epi, (k + 3) >> p.log_inner));
-                    }
-                    break;
+            for (uint32_t i = tid; i < rows_in * CV && i < (uint32_t)(R * CV); i += NT) {
+                const uint32_t cv = i & (CV - 1), d = i >> LCV;
+                const uint32_t r = (LR == 0) ? 0u : (__brev(d) >> (32 - LR));
+                const uint32_t lidx = d * ncols + col0 + 4u * cv;
+                uint4 v = smv[T::chunk(r, cv)];
+                if (p.log_inner >= 2) {
+                    v = mul4(v, pow_lookup(p.pro, lidx >> p.log_inner));
+                } else {
+                    v.x = pow_apply(p.pro, (lidx + 0) >> p.log_inner, v.x);
+                    v.y = pow_apply(p.pro, (lidx + 1) >> p.log_inner, v.y);
+                    v.z = pow_apply(p.pro, (lidx + 2) >> p.log_inner, v.z);
+                    v.w = pow_apply(p.pro, (lidx + 3) >> p.log_inner, v.w);
                 }
-                case EPI_CONST:
-                    v = mul4(v, p.epi_const);
-                    break;
-                default:
-                    v = make_uint4(min(v.x, v.x - P), min(v.y, v.y - P), min(v.z, v.z - P), min(v.w, v.w - P));
-                    break;
+                smv[T::chunk(r, cv)] = v;
             }
-            *reinterpret_cast<uint4*>(out + ((((size_t)j << LR) + e) << log_pfull) + low) = v;
+            __syncthreads();
         }
-    } else {
-        // pfull == 1 (first pass of a plain vector): column col is written as the contiguous run out[col*R + e];
-        // lanes walk e, so each of the four scalar stores of a chunk is coalesced
-#pragma unroll 2
-        for (int i = tid; i < R * CV; i += NT) {
-            const uint32_t e = i & (R - 1), cv = i >> LR;
-            uint4 v = smv[T::chunk(e, cv)];
-            const uint32_t col = col0 + 4u * cv;
-            if (p.epi_mode == EPI_TWIDDLE) {
-                v.x = monty_mul(v.x, pow_lookup(p.epi, ((col + 0) * e) << p.epi_shift));
-                v.y = monty_mul(v.y, pow_lookup(p.epi, ((col + 1) * e) << p.epi_shift));
-                v.z = monty_mul(v.z, pow_lookup(p.epi, ((col + 2) * e) << p.epi_shift));
-                v.w = monty_mul(v.w, pow_lookup(p.epi, ((col + 3) * e) << p.epi_shift));
-            } else if (p.epi_mode == EPI_CONST) {
-                v = mul4(v, p.epi_const);
-            } else {
-                v = make_uint4(min(v.x, v.x - P), min(v.y, v.y - P), min(v.z, v.z - P), min(v.w, v.w - P));
+
+        // ---- radix-16 DIT rounds, strides 1, 16, 256
+        if constexpr (T::G1 > 0) dit_round_v4<LR, LC, 0, T::G1>(smv, p);
+        if constexpr (T::G2 > 0) {
+            __syncthreads();
+            dit_round_v4<LR, LC, 4, T::G2>(smv, p);
+        }
+        if constexpr (T::G3 > 0) {
+            __syncthreads();
+            dit_round_v4<LR, LC, 8, T::G3>(smv, p);
+        }
+        __syncthreads();
+
+        // ---- epilogue + store
+        if (p.log_pfull >= 2) {
+            switch (p.epi_mode) {
+                case EPI_TWIDDLE: store_rows_v4<LR, LC, EPI_TWIDDLE>(smv, out, p, col0); break;
+                case EPI_OUTIDX: store_rows_v4<LR, LC, EPI_OUTIDX>(smv, out, p, col0); break;
+                case EPI_CONST: store_rows_v4<LR, LC, EPI_CONST>(smv, out, p, col0); break;
+                default: store_rows_v4<LR, LC, EPI_NONE>(smv, out, p, col0); break;
             }
-            uint32_t* o = out + ((size_t)col << LR) + e;
-            o[0] = v.x;
-            o[(size_t)1 << LR] = v.y;
-            o[(size_t)2 << LR] = v.z;
-            o[(size_t)3 << LR] = v.w;
+        } else {
+            switch (p.epi_mode) {
+                case EPI_TWIDDLE: store_cols_v4<LR, LC, EPI_TWIDDLE>(smv, out, p, col0); break;
+                case EPI_CONST: store_cols_v4<LR, LC, EPI_CONST>(smv, out, p, col0); break;
+                default: store_cols_v4<LR, LC, EPI_NONE>(smv, out, p, col0); break;
+            }
         }
+        __syncthreads();  // the buffer just read is the prefetch target of the next iteration
     }
 }
 
 template <int LR, int LC>
 void launch_pass_v4(const PassParams& p, dim3 grid, cudaStream_t s) {
     using T = V4<LR, LC>;
-    static bool configured[64] = {};
-    if (T::SMEM > 48 * 1024) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!configured[dev & 63]) {
-            cudaFuncSetAttribute(ntt_pass_v4_kernel<LR, LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
-            configured[dev & 63] = true;
-        }
+    constexpr bool DB = (2 * T::SMEM <= 96 * 1024);  // double buffering only where >= 2 CTAs still fit per SM
+    constexpr size_t smem = DB ? 2 * T::SMEM : T::SMEM;
+    static int ctas_per_sm[64] = {};
+    static int n_sm[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (ctas_per_sm[dev] == 0) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(ntt_pass_v4_kernel<LR, LC, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ntt_pass_v4_kernel<LR, LC, DB>, T::NT, smem);
+        cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+        ctas_per_sm[dev] = occ > 0 ? occ : 1;
     }
-    ntt_pass_v4_kernel<LR, LC><<<grid, T::NT, T::SMEM, s>>>(p);
+    const uint32_t tiles_x = grid.x, total = grid.x * grid.y;
+    uint32_t ctas = (uint32_t)(ctas_per_sm[dev] * n_sm[dev]);
+    if (ctas > total) ctas = total;
+    ntt_pass_v4_kernel<LR, LC, DB><<<ctas, T::NT, smem, s>>>(p, tiles_x, total);
 }
 
 }  // namespace bb
