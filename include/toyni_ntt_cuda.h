@@ -77,6 +77,14 @@ int bb_ntt_batch_device(uint32_t* d_data, uint32_t log_n, size_t batch, int dir)
  * transform_ext (src/math/domain.rs:140-151) in one go. */
 int bb_ntt_ext_device(uint32_t* d_data, uint32_t log_n, int dir);
 
+/* Building blocks of the sharded four-step NTT (n = n1*n2, input index j1*n2 + j2, output k1 + n1*k2; one rank
+ * owns a block of `cols` columns j2 of the n1 x n2 matrix):
+ *   bb_ntt_columns_device  - n1-point transforms down the columns of a row-major [2^log_n1][cols] block
+ *   bb_fourstep_twiddle_device - multiply element (k1, c) by w_n^((col_offset + c) * k1)
+ * The transpose between the two halves is an all-to-all owned by the caller (toyni_b200/multigpu.py, NCCL). */
+int bb_ntt_columns_device(uint32_t* d_block, uint32_t log_n1, size_t cols, int dir);
+int bb_fourstep_twiddle_device(uint32_t* d_block, uint32_t log_n, uint32_t log_n1, size_t cols, size_t col_offset, int dir);
+
 /* BabyBearDomain::fft on a coset (src/math/domain.rs:107-123,154-162): zero-pad/truncate the
  * n_coeffs coefficients to 2^log_size, multiply by shift^i, forward NTT.  Fused into the first
  * NTT pass: only the n_coeffs inputs are read.  shift == 1 is the plain domain.  d_out must not

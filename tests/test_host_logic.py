@@ -1,0 +1,111 @@
+"""Host-side logic that needs no GPU: Merkle openings over GPU-format node arrays, the sharding index maps of the
+multi-GPU layer (checked with a 2-rank gloo group on CPU), and the product's refusal to run without a device."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from toyni_b200 import merkle as M
+from toyni_b200 import multigpu as MG
+from toyni_b200.lib import ToyniCudaError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_salted_tree_openings_verify_against_oracle_nodes():
+    n = 37
+    vals = O.random_field(n, seed=1)
+    salts = O.random_bytes(16 * n, seed=2).reshape(n, 16)
+    nodes, root = O.commit_values(vals, salts)
+    tree = M.SaltedTree(n, nodes, root, salts)  # same node layout the GPU commit produces
+    for i in (0, 1, 17, 35, 36):
+        proof = tree.get_proof(i)
+        leaf = salts[i].tobytes() + int(vals[i]).to_bytes(8, "little")
+        assert M.verify_merkle_proof(leaf, proof, root)
+        path, pos = O.merkle_open(nodes, n, i)
+        assert [p.tobytes() for p in path] == proof.path and [bool(b) for b in pos] == proof.position
+        assert not M.verify_merkle_proof(leaf[:-1] + b"\x00", proof, root) or leaf[-1] == 0
+    assert tree.get_proof(n) is None
+
+
+def test_fourstep_index_maps_cpu_simulation():
+    """The sharded 2^k four-step NTT as pure index arithmetic (numpy, oracle transforms per shard)."""
+    for log_n, G in ((6, 2), (8, 4), (10, 8)):
+        n = 1 << log_n
+        x = O.random_field(n, seed=log_n)
+        got = MG.fourstep_reference_simulation(x, G, ntt=O.ntt, mul=lambda a, b: (a.astype(object) * b.astype(object) % O.P).astype(np.uint64))
+        assert np.array_equal(got, O.ntt(x)), (log_n, G)
+
+
+def test_cyclic_fold_layout_is_closed():
+    for G in (1, 2, 4, 8):
+        m = 1 << 10
+        ev = O.random_field(m, seed=G)
+        xs = O.domain_elements(m, 7)
+        full = O.fri_fold(ev, xs, 31337)
+        for r in range(G):
+            local = ev[r::G]
+            half = local.size // 2
+            # pair (t, t+half) of the shard is the global pair (i, i + m/2)
+            idx = r + G * np.arange(half)
+            assert np.array_equal(local[:half], ev[idx]) and np.array_equal(local[half:], ev[idx + m // 2])
+            assert np.array_equal(full[r::G], O.fri_fold(np.concatenate([ev[idx], ev[idx + m // 2]]), xs[idx], 31337))
+
+
+_GLOO_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from oracle import oracle as O
+from toyni_b200 import multigpu as MG
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+log_n = 10
+n = 1 << log_n
+x = O.random_field(n, seed=7)
+# every rank owns its column block of the n1 x n2 matrix; local transforms by the oracle (no GPU here)
+out = MG.fourstep_ntt_distributed(x, rank, world, backend_ntt=lambda a: O.ntt(a), device="cpu")
+ref = O.ntt(x)
+n1 = MG.fourstep_split(log_n, world)[0]
+k1 = np.arange(rank * n1 // world, (rank + 1) * n1 // world)
+mine = ref.reshape(n // n1, n1)[:, k1].T   # out[k1_local][k2] = X[k1 + n1*k2]
+assert np.array_equal(out, mine), "rank %d mismatch" % rank
+dist.barrier()
+if rank == 0: print("gloo fourstep ok")
+dist.destroy_process_group()
+"""
+
+
+def test_fourstep_all_to_all_with_gloo_world_size_2(tmp_path):
+    script = tmp_path / "gloo_fourstep.py"
+    script.write_text(_GLOO_SCRIPT.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29511")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29511", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "gloo fourstep ok" in out.stdout
+
+
+def test_product_path_refuses_to_run_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from toyni_b200 import domain, ntt
+    with pytest.raises(ToyniCudaError):
+        ntt.ntt_cuda(np.arange(8, dtype=np.uint64))
+    with pytest.raises(ToyniCudaError):
+        domain.BabyBearDomain(8).fft(np.arange(8, dtype=np.uint64))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "toyni_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/", "").lower() or f == "__init__.py" or "import oracle" not in text
+                assert "from oracle" not in text and "import oracle" not in text and "toyni_oracle" not in text, f

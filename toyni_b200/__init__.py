@@ -9,4 +9,4 @@ Host-side mirror of the reference's interfaces for this path:
   multigpu.py — sharded NTT / fold chain over torch.distributed (NCCL)
 All compute goes through libntt_cuda.so (toyni_b200/csrc); there is no CPU fallback.
 """
-from .lib import P, lib, library_path  # noqa: F401
+from .lib import P, library_path  # noqa: F401

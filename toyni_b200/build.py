@@ -13,7 +13,7 @@ NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-diag-suppress", "186,128"]
 SOURCES = ["ntt_v4_inst_d.cu", "ntt_v4_inst_c.cu", "ntt_v4_inst_b.cu", "ntt_v4_inst_a.cu", "ntt_inst_a.cu", "ntt_inst_b.cu", "ntt_inst_c.cu", "ntt_inst_d.cu", "ntt_dispatch.cu", "ntt_engine.cu",
-           "fri_fold.cu", "merkle.cu", "c_abi.cu"]
+           "fri_fold.cu", "elementwise.cu", "merkle.cu", "c_abi.cu"]
 SO = os.path.join(HERE, "libntt_cuda.so")
 AR = os.path.join(HERE, "libntt_cuda.a")
 
@@ -45,7 +45,7 @@ def build(verbose=False, force=False):
         objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
     newest = max(os.path.getmtime(o) for o in objs)
     if force or not os.path.exists(SO) or os.path.getmtime(SO) < newest:
-        subprocess.check_call([NVCC, "-shared", "-cudart", "shared", "-o", SO] + objs)
+        subprocess.check_call([NVCC, "-shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO] + objs)
         if os.path.exists(AR):
             os.remove(AR)
         subprocess.check_call(["ar", "rcs", AR] + objs)

@@ -211,6 +211,16 @@ int bb_ntt_ext_device(uint32_t* d_data, uint32_t log_n, int dir) {
     return run_ntt(d_data, d_data, log_n, 2, (size_t)1 << log_n, 1, dir, 1);
 }
 
+int bb_ntt_columns_device(uint32_t* d_block, uint32_t log_n1, size_t cols, int dir) {
+    if (!is_pow2(cols)) return note((int)cudaErrorInvalidValue);
+    return run_ntt(d_block, d_block, log_n1, (int)log2_of(cols), (size_t)1 << log_n1, 1, dir, 1);
+}
+int bb_fourstep_twiddle_device(uint32_t* d_block, uint32_t log_n, uint32_t log_n1, size_t cols, size_t col_offset, int dir) {
+    CK(fourstep_twiddle(d_block, (int)log_n, (int)log_n1, cols, col_offset, dir == 1, cur_stream()));
+    g_launches++;
+    return 0;
+}
+
 int bb_coset_fft_device(const uint32_t* d_coeffs, size_t n_coeffs, uint32_t log_size, uint32_t shift, int limbs,
                         uint32_t* d_out) {
     if ((limbs != 1 && limbs != 4) || shift == 0 || shift >= P) return note((int)cudaErrorInvalidValue);

@@ -14,6 +14,8 @@ int fri_fold_coset(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int li
 // Reference signature: arbitrary evaluation points xs[0..m/2) on the device.
 int fri_fold_xs(const uint32_t* d_in, const uint32_t* d_xs, uint32_t* d_out, size_t m, int limbs, const uint32_t beta[4],
                 cudaStream_t s);
+// four-step NTT, step 2: d[k1][c] *= w_n^((col_offset + c) * k1) over a local block of 2^log_n1 rows x cols columns
+int fourstep_twiddle(uint32_t* d, int log_n, int log_n1, size_t cols, size_t col_offset, bool inverse, cudaStream_t s);
 // cached g^t tables (shared with the NTT engine)
 int engine_pow_table(uint32_t g, int log_total, uint32_t scale, PowTable* out);
 }  // namespace bb

@@ -39,6 +39,8 @@ _SIGNATURES = {
     "bb_ntt_device": ([C.c_void_p, C.c_uint32, C.c_int], C.c_int),
     "bb_ntt_batch_device": ([C.c_void_p, C.c_uint32, C.c_size_t, C.c_int], C.c_int),
     "bb_ntt_ext_device": ([C.c_void_p, C.c_uint32, C.c_int], C.c_int),
+    "bb_ntt_columns_device": ([C.c_void_p, C.c_uint32, C.c_size_t, C.c_int], C.c_int),
+    "bb_fourstep_twiddle_device": ([C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_size_t, C.c_int], C.c_int),
     "bb_coset_fft_device": ([C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p], C.c_int),
     "bb_coset_ifft_device": ([C.c_void_p, C.c_uint32, C.c_uint32, C.c_int], C.c_int),
     "bb_fri_fold_device": ([C.c_void_p, C.c_size_t, C.c_uint32, u32p, C.c_int, C.c_void_p], C.c_int),

@@ -1,0 +1,181 @@
+"""Sharding of the hot path over the GPUs of one box (one process per GPU, torch.distributed).
+
+Nothing like this exists in the reference (single device, default stream).  Three layouts:
+
+* independent column NTTs (batched traces): column c lives on rank c % G — no communication at all;
+* one large NTT (2^25..2^27): four-step.  n = n1*n2, input index j = j1*n2 + j2, output index k = k1 + n1*k2.
+  Rank r owns the column block j2 in [r*n2/G, (r+1)*n2/G) of the n1 x n2 input matrix (all j1) and ends up with
+  the row block k1 in [r*n1/G, (r+1)*n1/G) of the output matrix out[k1][k2] = X[k1 + n1*k2] (all k2):
+      1. n1-point NTTs down the local columns            (bb_ntt_columns_device)
+      2. multiply (k1, j2) by w_n^(j2*k1)                (bb_fourstep_twiddle_device)
+      3. all-to-all: row block s of every rank goes to rank s  (the only exchange: n/G^2 values per peer)
+      4. n2-point NTTs along the local rows              (bb_ntt_batch_device)
+* FRI folding: cyclic layout, rank r owns indices i = r (mod G).  The fold partner i + m/2 is on the same rank
+  while m/2 >= G, so a 2^25 -> 2^4 chain needs no exchange for G <= 8 (bb_fri_fold_shard_device).
+
+The index arithmetic is written once (`fourstep_*`) and runs either on CUDA tensors with NCCL or on CPU tensors
+with gloo, which is how the N > 1 path is tested without GPUs.
+"""
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .lib import P
+
+
+def fourstep_split(log_n, world):
+    """(n1, n2) with n1*n2 = 2^log_n, both divisible by `world`; n1 >= n2."""
+    l1 = (log_n + 1) // 2
+    n1, n2 = 1 << l1, 1 << (log_n - l1)
+    assert n1 % world == 0 and n2 % world == 0, "transform too small for this many ranks"
+    return n1, n2
+
+
+def fourstep_scatter(x, rank, world):
+    """Local input block of `rank`: columns j2 in its range, all rows j1, row-major (n1, n2/G)."""
+    n = x.size
+    n1, n2 = fourstep_split(n.bit_length() - 1, world)
+    w = n2 // world
+    return np.ascontiguousarray(x.reshape(n1, n2)[:, rank * w:(rank + 1) * w])
+
+
+def fourstep_gather(blocks, log_n):
+    """Natural-order X from the per-rank output blocks out_r[k1_local][k2] = X[k1 + n1*k2]."""
+    world = len(blocks)
+    n1, n2 = fourstep_split(log_n, world)
+    full = np.concatenate(blocks, axis=0)  # (n1, n2) indexed [k1][k2]
+    return np.ascontiguousarray(full.T).reshape(-1)  # index k1 + n1*k2
+
+
+def fourstep_reference_simulation(x, world, ntt, mul):
+    """All ranks simulated in one process with plain numpy: pins the index maps against a 1-D transform."""
+    n = x.size
+    log_n = n.bit_length() - 1
+    n1, n2 = fourstep_split(log_n, world)
+    w_n = pow(440564289, 1 << (27 - log_n), P)
+    cw, rw = n2 // world, n1 // world
+    stage = []
+    for r in range(world):
+        a = fourstep_scatter(x, r, world)
+        a = np.stack([ntt(np.ascontiguousarray(a[:, c])) for c in range(cw)], axis=1)        # step 1
+        tw = np.array([[pow(w_n, (r * cw + c) * k1, P) for c in range(cw)] for k1 in range(n1)], dtype=np.uint64)
+        stage.append(mul(a, tw))                                                             # step 2
+    outs = []
+    for r in range(world):                                                                   # step 3 (exchange)
+        b = np.concatenate([stage[s][r * rw:(r + 1) * rw, :] for s in range(world)], axis=1)  # (n1/G, n2)
+        outs.append(np.stack([ntt(np.ascontiguousarray(b[k])) for k in range(rw)], axis=0))  # step 4
+    return fourstep_gather(outs, log_n)
+
+
+def _all_to_all_rows(block, world):
+    """block: (n1, cols) tensor; row block s goes to rank s.  Returns (n1/G, G*cols): my rows, all columns."""
+    n1, cols = block.shape
+    rw = n1 // world
+    if world == 1:
+        return block
+    recv = torch.empty_like(block)
+    dist.all_to_all_single(recv.view(-1), block.contiguous().view(-1))
+    # recv is [source s][k1_local][c]; the row transforms want [k1_local][s][c]
+    return recv.view(world, rw, cols).permute(1, 0, 2).reshape(rw, world * cols).contiguous()
+
+
+def fourstep_ntt_distributed(x_full, rank, world, backend_ntt, device="cpu"):
+    """CPU/gloo form used by the tests: local transforms through `backend_ntt` (a 1-D natural-order NTT),
+    exchange through torch.distributed.  Returns this rank's output block as numpy (n1/G, n2)."""
+    n = x_full.size
+    log_n = n.bit_length() - 1
+    n1, n2 = fourstep_split(log_n, world)
+    cw = n2 // world
+    a = fourstep_scatter(x_full, rank, world)
+    a = np.stack([backend_ntt(np.ascontiguousarray(a[:, c])) for c in range(cw)], axis=1)
+    w_n = pow(440564289, 1 << (27 - log_n), P)
+    tw = np.array([[pow(w_n, (rank * cw + c) * k1, P) for c in range(cw)] for k1 in range(n1)], dtype=object)
+    a = (a.astype(object) * tw % P).astype(np.int64)
+    b = _all_to_all_rows(torch.from_numpy(a).to(device), world).cpu().numpy().astype(np.uint64)
+    return np.stack([backend_ntt(np.ascontiguousarray(b[k])) for k in range(b.shape[0])], axis=0)
+
+
+# ------------------------------------------------------------------------------------------------ CUDA / NCCL
+def fourstep_ntt_cuda(block, log_n, rank, world, inverse=False):
+    """One 2^log_n NTT sharded over `world` GPUs.  block: int32 CUDA tensor (n1, n2/G), this rank's columns.
+    Returns (n1/G, n2): out[k1_local][k2] = X[k1 + n1*k2].  Device kernels through the C ABI; the exchange is one
+    NCCL all-to-all (world == 1 runs the same steps without it)."""
+    import ctypes as C
+
+    from .device import _bind_stream, _chk, ntt_batch_
+    from .lib import check, lib
+
+    n1, n2 = fourstep_split(log_n, world)
+    cw = n2 // world
+    assert tuple(block.shape) == (n1, cw)
+    _bind_stream()
+    d = 1 if inverse else 0
+    check(lib().bb_ntt_columns_device(_chk(block), n1.bit_length() - 1, cw, d), "bb_ntt_columns_device")
+    check(lib().bb_fourstep_twiddle_device(_chk(block), log_n, n1.bit_length() - 1, cw, rank * cw, d),
+          "bb_fourstep_twiddle_device")
+    rows = _all_to_all_rows(block, world)
+    return ntt_batch_(rows, inverse)
+
+
+def fold_chain_cuda(local, log_m, shift, betas, rank, world, until=16):
+    """FRI fold chain on one cyclic shard (global indices rank, rank+G, ...), betas supplied up front.
+    Returns the list of local layers.  No communication while the layer has at least 2*world values."""
+    from .device import fri_fold_shard
+
+    layers = [local]
+    x0 = shift % P
+    k = 0
+    m = 1 << log_m
+    while m > until and (m // 2) >= world:
+        nxt = fri_fold_shard(layers[-1], log_m - k, x0, betas[k], world, rank)
+        layers.append(nxt)
+        x0 = x0 * x0 % P
+        m //= 2
+        k += 1
+    return layers
+
+
+def bench_fourstep(args, rank, world, dev, log_n=27):
+    """bench.py --workload fourstep27: ONE 2^27 forward NTT per step over all ranks (strong scaling)."""
+    import json
+
+    n = 1 << log_n
+    n1, n2 = fourstep_split(log_n, world)
+    cw = n2 // world
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x70796E69 + rank)
+    blocks = [torch.randint(0, P, (n1, cw), dtype=torch.int32, device=dev, generator=g) for _ in range(2)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        fourstep_ntt_cuda(blocks[i % 2].clone(), log_n, rank, world)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    work = [blocks[i % 2].clone() for i in range(min(args.steps, 4))]
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        fourstep_ntt_cuda(work[i % len(work)], log_n, rank, world)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        sent = (n // world) * (world - 1) // world * 4
+        print(json.dumps({
+            "metric": f"babybear_ntt_2^{log_n}_fourstep_throughput", "value": n * args.steps / (ms * 1e-3) / 1e9,
+            "unit": "Gelem/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"one forward 2^{log_n} NTT, four-step, column blocks over {world} GPUs",
+                       "n1": n1, "n2": n2, "nvlink_bytes_sent_per_gpu_per_step": sent,
+                       "l2": "each rank's block is 2^27/G x 4 B (>= 64 MiB), rotated over buffers"},
+        }), flush=True)
