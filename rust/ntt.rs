@@ -1,0 +1,266 @@
+// src/ntt.rs — drop-in replacement for the reference file of the same name (jonas089/toyni), written against the
+// B200-native library in this repository (include/toyni_ntt_cuda.h).  NOT COMPILED HERE: this image has no Rust
+// toolchain; the same C ABI is exercised from Python (toyni_b200/ntt.py) and by tests/.
+//
+// Public surface kept exactly: `ntt`, `intt`, `roots_of_unity_domain` (CPU, unchanged), and with `--features cuda`
+// `cuda_available`, `ntt_cuda`, `intt_cuda`, `CudaBuffer`.  Added (same feature): `coset_fft_cuda`,
+// `coset_ifft_cuda`, `fri_fold_cuda`, `fri_fold_ext_cuda`, `merkle_commit_cuda`, which the call sites in
+// src/math/domain.rs, src/math/fri.rs and src/fibonacci.rs use behind their existing `use_gpu` flag.
+
+use crate::babybear::BabyBear;
+
+// ── CPU NTT (always available; identical to the reference, src/ntt.rs:14-81) ────────────────
+#[inline]
+fn bit_reverse(mut x: usize, log_n: usize) -> usize {
+    let mut r = 0;
+    for _ in 0..log_n {
+        r = (r << 1) | (x & 1);
+        x >>= 1;
+    }
+    r
+}
+
+pub fn ntt(values: &mut [BabyBear], omega: BabyBear) {
+    let n = values.len();
+    assert!(n.is_power_of_two(), "NTT size must be power of 2");
+    let log_n = n.trailing_zeros() as usize;
+    for i in 0..n {
+        let j = bit_reverse(i, log_n);
+        if i < j {
+            values.swap(i, j);
+        }
+    }
+    let mut len = 2;
+    while len <= n {
+        let w_len = omega.pow((n / len) as u64);
+        for i in (0..n).step_by(len) {
+            let mut w = BabyBear::one();
+            for j in 0..len / 2 {
+                let u = values[i + j];
+                let v = values[i + j + len / 2] * w;
+                values[i + j] = u + v;
+                values[i + j + len / 2] = u - v;
+                w = w * w_len;
+            }
+        }
+        len *= 2;
+    }
+}
+
+pub fn intt(values: &mut [BabyBear], omega: BabyBear) {
+    let n = values.len();
+    ntt(values, omega.pow(n as u64 - 1));
+    let inv_n = BabyBear::new(n as u64).inverse();
+    for v in values.iter_mut() {
+        *v = *v * inv_n;
+    }
+}
+
+pub fn roots_of_unity_domain(n: usize) -> Vec<BabyBear> {
+    assert!(n.is_power_of_two(), "Domain size must be power of 2");
+    let omega = BabyBear::get_root_of_unity(n.trailing_zeros());
+    let mut domain = Vec::with_capacity(n);
+    let mut cur = BabyBear::one();
+    for _ in 0..n {
+        domain.push(cur);
+        cur = cur * omega;
+    }
+    domain
+}
+
+// ── CUDA path (feature = "cuda") ─────────────────────────────────────────────────────────────
+#[cfg(feature = "cuda")]
+mod cuda {
+    use super::BabyBear;
+    use crate::ext::Ext;
+    use std::ffi::{c_void, CStr};
+    use std::os::raw::c_char;
+
+    type CudaError = i32;
+    const CUDA_SUCCESS: CudaError = 0;
+
+    #[link(name = "ntt_cuda", kind = "static")]
+    unsafe extern "C" {
+        // unchanged from the reference (src/ntt.rs:96-110)
+        fn cuda_copy_to_device(d_dest: *mut u64, h_src: *const u64, count: usize) -> CudaError;
+        fn cuda_copy_from_device(h_dest: *mut u64, d_src: *const u64, count: usize) -> CudaError;
+        fn cuda_malloc(d_ptr: *mut *mut u64, count: usize) -> CudaError;
+        fn cuda_free(d_ptr: *mut u64) -> CudaError;
+        fn cuda_get_error_string(error: CudaError) -> *const c_char;
+        fn cudaGetDeviceCount(count: *mut i32) -> CudaError;
+        fn ntt_ctx_create(n: u32) -> *mut c_void;
+        fn ntt_run_inplace(ctx: *mut c_void, h_data: *mut u64);
+        fn intt_run_inplace(ctx: *mut c_void, h_data: *mut u64);
+        // new in the B200 library (include/toyni_ntt_cuda.h, sections 2-3)
+        fn bb_last_error() -> CudaError;
+        fn bb_clear_error();
+        fn bb_device_ok() -> i32;
+        fn toyni_domain_fft(coeffs: *const u64, n_coeffs: usize, size: usize, shift: u64, out: *mut u64) -> CudaError;
+        fn toyni_domain_ifft(evals: *const u64, size: usize, shift: u64, out: *mut u64) -> CudaError;
+        fn toyni_domain_fft_ext(coeffs: *const u64, n_coeffs: usize, size: usize, shift: u64, out: *mut u64) -> CudaError;
+        fn toyni_domain_ifft_ext(evals: *const u64, size: usize, shift: u64, out: *mut u64) -> CudaError;
+        fn toyni_fri_fold(evals: *const u64, m: usize, xs: *const u64, beta: u64, out: *mut u64) -> CudaError;
+        fn toyni_fri_fold_ext(evals: *const u64, m: usize, xs: *const u64, beta: *const u64, out: *mut u64) -> CudaError;
+        fn toyni_merkle_commit(values: *const u64, n: usize, limbs: i32, salts: *const u8, nodes_out: *mut u8,
+                               root_out: *mut u8) -> CudaError;
+        fn bb_merkle_node_count(nleaves: usize) -> usize;
+    }
+
+    // BabyBear is `#[repr(C)] { value: u64 }` and Ext is `#[repr(C)] { c: [BabyBear; 4] }`
+    const _: () = assert!(std::mem::size_of::<BabyBear>() == 8 && std::mem::align_of::<BabyBear>() == 8);
+    const _: () = assert!(std::mem::size_of::<Ext>() == 32);
+
+    struct CtxPtr(*mut c_void);
+    unsafe impl Send for CtxPtr {}
+    unsafe impl Sync for CtxPtr {}
+
+    fn err_string(e: CudaError) -> String {
+        unsafe { CStr::from_ptr(cuda_get_error_string(e)).to_string_lossy().into_owned() }
+    }
+
+    fn get_or_create_ctx(n: usize) -> Result<*mut c_void, String> {
+        use std::collections::HashMap;
+        use std::sync::{Mutex, OnceLock};
+        static CACHE: OnceLock<Mutex<HashMap<usize, CtxPtr>>> = OnceLock::new();
+        let mut guard = CACHE.get_or_init(|| Mutex::new(HashMap::new())).lock().unwrap();
+        if let Some(p) = guard.get(&n) {
+            return Ok(p.0);
+        }
+        let ptr = unsafe { ntt_ctx_create(n as u32) };
+        if ptr.is_null() {
+            // the reference caches a null context unchecked (src/ntt.rs:138-139); this one reports it
+            return Err(format!("ntt_ctx_create({n}) failed: {}", err_string(unsafe { bb_last_error() })));
+        }
+        guard.insert(n, CtxPtr(ptr));
+        Ok(ptr)
+    }
+
+    /// True iff a CUDA device is present AND it can run this library (sm_100 only, no PTX fallback).
+    pub fn cuda_available() -> bool {
+        unsafe {
+            let mut count = 0;
+            cudaGetDeviceCount(&mut count) == CUDA_SUCCESS && count > 0 && bb_device_ok() == 1
+        }
+    }
+
+    pub struct CudaBuffer {
+        ptr: *mut u64,
+        size: usize,
+    }
+
+    impl CudaBuffer {
+        pub fn new(size: usize) -> Result<Self, String> {
+            let mut ptr: *mut u64 = std::ptr::null_mut();
+            let err = unsafe { cuda_malloc(&mut ptr, size) };
+            if err != CUDA_SUCCESS {
+                return Err(format!("CUDA malloc failed: {}", err_string(err)));
+            }
+            Ok(Self { ptr, size })
+        }
+        pub fn copy_from_host(&mut self, data: &[u64]) -> Result<(), String> {
+            assert_eq!(data.len(), self.size, "Size mismatch");
+            let err = unsafe { cuda_copy_to_device(self.ptr, data.as_ptr(), self.size) };
+            if err != CUDA_SUCCESS {
+                return Err(format!("CUDA copy to device failed: {}", err_string(err)));
+            }
+            Ok(())
+        }
+        pub fn copy_to_host(&self, data: &mut [u64]) -> Result<(), String> {
+            assert_eq!(data.len(), self.size, "Size mismatch");
+            let err = unsafe { cuda_copy_from_device(data.as_mut_ptr(), self.ptr, self.size) };
+            if err != CUDA_SUCCESS {
+                return Err(format!("CUDA copy from device failed: {}", err_string(err)));
+            }
+            Ok(())
+        }
+        pub fn as_ptr(&self) -> *mut u64 {
+            self.ptr
+        }
+    }
+    impl Drop for CudaBuffer {
+        fn drop(&mut self) {
+            unsafe {
+                cuda_free(self.ptr);
+            }
+        }
+    }
+    unsafe impl Send for CudaBuffer {}
+    unsafe impl Sync for CudaBuffer {}
+
+    fn run(values: &mut [BabyBear], inverse: bool) -> Result<(), String> {
+        if !cuda_available() {
+            return Err("CUDA not available".to_string());
+        }
+        let n = values.len();
+        assert!(n.is_power_of_two(), "NTT size must be power of 2");
+        assert!(n.trailing_zeros() <= 27, "BabyBear only supports NTT up to 2^27");
+        let ctx = get_or_create_ctx(n)?;
+        let raw = values.as_mut_ptr() as *mut u64;
+        unsafe {
+            bb_clear_error();
+            if inverse { intt_run_inplace(ctx, raw) } else { ntt_run_inplace(ctx, raw) }
+            match bb_last_error() {
+                CUDA_SUCCESS => Ok(()),
+                e => Err(format!("CUDA NTT failed: {}", err_string(e))),
+            }
+        }
+    }
+
+    pub fn ntt_cuda(values: &mut [BabyBear]) -> Result<(), String> { run(values, false) }
+    pub fn intt_cuda(values: &mut [BabyBear]) -> Result<(), String> { run(values, true) }
+
+    fn ck(e: CudaError, what: &str) -> Result<(), String> {
+        if e == CUDA_SUCCESS { Ok(()) } else { Err(format!("{what} failed: {}", err_string(e))) }
+    }
+
+    /// BabyBearDomain::fft with the coset shift fused on the device (src/math/domain.rs:107-123).
+    pub fn coset_fft_cuda(coeffs: &[BabyBear], size: usize, shift: BabyBear) -> Result<Vec<BabyBear>, String> {
+        let mut out = vec![BabyBear::zero(); size];
+        ck(unsafe { toyni_domain_fft(coeffs.as_ptr() as *const u64, coeffs.len(), size, shift.value, out.as_mut_ptr() as *mut u64) }, "CUDA NTT")?;
+        Ok(out)
+    }
+    /// BabyBearDomain::ifft (src/math/domain.rs:85-102).
+    pub fn coset_ifft_cuda(evals: &[BabyBear], shift: BabyBear) -> Result<Vec<BabyBear>, String> {
+        let mut out = vec![BabyBear::zero(); evals.len()];
+        ck(unsafe { toyni_domain_ifft(evals.as_ptr() as *const u64, evals.len(), shift.value, out.as_mut_ptr() as *mut u64) }, "CUDA INTT")?;
+        Ok(out)
+    }
+    pub fn coset_fft_ext_cuda(coeffs: &[Ext], size: usize, shift: BabyBear) -> Result<Vec<Ext>, String> {
+        let mut out = vec![Ext::zero(); size];
+        ck(unsafe { toyni_domain_fft_ext(coeffs.as_ptr() as *const u64, coeffs.len(), size, shift.value, out.as_mut_ptr() as *mut u64) }, "CUDA NTT")?;
+        Ok(out)
+    }
+    pub fn coset_ifft_ext_cuda(evals: &[Ext], shift: BabyBear) -> Result<Vec<Ext>, String> {
+        let mut out = vec![Ext::zero(); evals.len()];
+        ck(unsafe { toyni_domain_ifft_ext(evals.as_ptr() as *const u64, evals.len(), shift.value, out.as_mut_ptr() as *mut u64) }, "CUDA INTT")?;
+        Ok(out)
+    }
+    /// fri_fold / fri_fold_ext (src/math/fri.rs:27, :7)
+    pub fn fri_fold_cuda(evals: &[BabyBear], xs: &[BabyBear], beta: BabyBear) -> Result<Vec<BabyBear>, String> {
+        assert!(evals.len() % 2 == 0, "Evaluations length must be even");
+        let mut out = vec![BabyBear::zero(); evals.len() / 2];
+        ck(unsafe { toyni_fri_fold(evals.as_ptr() as *const u64, evals.len(), xs.as_ptr() as *const u64, beta.value, out.as_mut_ptr() as *mut u64) }, "CUDA fold")?;
+        Ok(out)
+    }
+    pub fn fri_fold_ext_cuda(evals: &[Ext], xs: &[BabyBear], beta: Ext) -> Result<Vec<Ext>, String> {
+        assert!(evals.len() % 2 == 0, "Evaluations length must be even");
+        let mut out = vec![Ext::zero(); evals.len() / 2];
+        ck(unsafe { toyni_fri_fold_ext(evals.as_ptr() as *const u64, evals.len(), xs.as_ptr() as *const u64, beta.c.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) }, "CUDA fold")?;
+        Ok(out)
+    }
+    /// build_merkle_tree / build_unsalted_tree (src/fibonacci.rs:340-363): every level, leaf level first, 32 B each.
+    pub fn merkle_commit_cuda(evals: &[BabyBear], salts: Option<&[[u8; 16]]>) -> Result<(Vec<u8>, [u8; 32]), String> {
+        let n = evals.len();
+        let mut nodes = vec![0u8; unsafe { bb_merkle_node_count(n) } * 32];
+        let mut root = [0u8; 32];
+        let sp = salts.map(|s| s.as_ptr() as *const u8).unwrap_or(std::ptr::null());
+        ck(unsafe { toyni_merkle_commit(evals.as_ptr() as *const u64, n, 1, sp, nodes.as_mut_ptr(), root.as_mut_ptr()) }, "CUDA Merkle commit")?;
+        Ok((nodes, root))
+    }
+}
+
+#[cfg(feature = "cuda")]
+pub use cuda::{
+    coset_fft_cuda, coset_fft_ext_cuda, coset_ifft_cuda, coset_ifft_ext_cuda, cuda_available, fri_fold_cuda,
+    fri_fold_ext_cuda, intt_cuda, merkle_commit_cuda, ntt_cuda, CudaBuffer,
+};
