@@ -32,6 +32,7 @@ struct V4 {
     static constexpr int CHUNKS = R * CV;
     static constexpr int RS = NT >> LCV;  // rows covered by one sweep of the CTA over chunks (when > 0)
     static constexpr size_t SMEM = (size_t)R * C * 4;
+    static constexpr size_t TW_BYTES = (R >= 32) ? (size_t)(R / 2) * 8 : 0;  // omega_R^i, i < R/2, as Shoup pairs
 
     // physical 16-byte chunk index of (row, cv); GF(2)-linear in its arguments
     __host__ __device__ static constexpr uint32_t chunk(uint32_t row, uint32_t cv) {
@@ -72,13 +73,12 @@ struct Vec<2> {
 };
 
 template <int LR, int LC, int S_LOG, int G_LOG>
-BB_D void dit_round_v4(uint4* __restrict__ sm, const PassParams& p) {
+BB_D void dit_round_v4(uint4* __restrict__ sm, const uint2* __restrict__ stw, const PassParams& p) {
     using T = V4<LR, LC>;
     constexpr int R = T::R, NT = T::NT, S = 1 << S_LOG, G = 1 << G_LOG, VW = T::VW;
     constexpr int CW = T::C / VW;  // items per row
     constexpr int ITEMS = (R / G) * CW;
     typedef typename Vec<VW>::type vec_t;
-    const char* __restrict__ twb = reinterpret_cast<const char*>(p.tw);
     vec_t* __restrict__ smw = reinterpret_cast<vec_t*>(sm);
 #pragma unroll 1
     for (int it = threadIdx.x; it < ITEMS; it += NT) {
@@ -100,9 +100,10 @@ BB_D void dit_round_v4(uint4* __restrict__ sm, const PassParams& p) {
         }
 #pragma unroll
         for (int t = 0; t < G_LOG; t++) {
-            // stage t twiddle kp is omega_4096^((b + kp*S) << sh): one base address per stage, kp folds into the offset
-            const int sh = (S_LOG == 0) ? 0 : (LOG_TW - (S_LOG + t + 1));
-            const char* tws = twb + ((size_t)(b << sh) << 3);
+            // stage t twiddle kp is omega_R^((b + kp*S) << sh), read from the CTA's shared-memory copy of the table:
+            // one base address per stage, kp folds into the immediate offset
+            const int sh = (S_LOG == 0) ? 0 : (LR - (S_LOG + t + 1));
+            const uint2* tws = stw + (b << sh);
 #pragma unroll
             for (int k = 0; k < G; k++) {
                 if (k & (1 << t)) continue;
@@ -117,7 +118,7 @@ BB_D void dit_round_v4(uint4* __restrict__ sm, const PassParams& p) {
                         for (int c = 0; c < VW; c++) bfly(x[k][c], x[k + (1 << t)][c], w);
                     }
                 } else {
-                    const uint2 w = __ldg(reinterpret_cast<const uint2*>(tws + ((size_t)((kp * S) << sh) << 3)));
+                    const uint2 w = tws[(kp * S) << sh];
 #pragma unroll
                     for (int c = 0; c < VW; c++) bfly(x[k][c], x[k + (1 << t)][c], w);
                 }
@@ -185,7 +186,8 @@ BB_D void store_rows_v4(const uint4* __restrict__ smv, uint32_t* __restrict__ ou
                 } else {
                     v = canon4(v);
                 }
-                *reinterpret_cast<uint4*>(o + (size_t)it * step) = v;
+                *reinterpret_cast<uint4*>(o) = v;
+                o += step;
             }
             return;
         }
@@ -299,13 +301,18 @@ BB_D void load_tile_v4(uint4* __restrict__ buf, const uint32_t* __restrict__ in,
             const uint32_t cv = tid & (CV - 1), r0 = tid >> LCV;
             const uint32_t sm0 = smem_u32(buf), cbase = T::chunk(r0, cv);
             const uint32_t d0 = (LR == 0) ? 0u : (__brev(r0) >> (32 - LR));
-            const uint32_t* src0 = in + (size_t)d0 * ncols + col0 + 4u * cv;
+            // row r0 | it*RS (disjoint bits): the swizzle and the bit reversal split into thread part ^ constant.
+            // brev(it*RS) runs over 0..NIT-1, so the NIT source rows are src0 + k*ncols: built by pointer increments
+            // (64-bit multiplies would occupy the FMA-heavy pipe, which the butterflies need)
+            constexpr int NIT = T::CHUNKS / NT;
+            const uint32_t* rowp[NIT];
+            rowp[0] = in + (size_t)d0 * ncols + col0 + 4u * cv;
 #pragma unroll
-            for (int it = 0; it < T::CHUNKS / NT; it++) {
-                // row r0 | it*RS (disjoint bits): the swizzle and the bit reversal split into thread part ^ constant
-                const uint32_t* src = src0 + (size_t)T::brev((uint32_t)(it * T::RS)) * ncols;
+            for (int k = 1; k < NIT; k++) rowp[k] = rowp[k - 1] + ncols;
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sm0 + ((cbase ^ T::chunk((uint32_t)(it * T::RS), 0)) << 4)),
-                             "l"(src)
+                             "l"(rowp[T::brev((uint32_t)(it * T::RS))])
                              : "memory");
             }
             return;
@@ -338,6 +345,12 @@ __global__ void __launch_bounds__(V4<LR, LC>::NT) ntt_pass_v4_kernel(const PassP
     const uint32_t ncols = p.ncols;
     uint32_t tile = blockIdx.x;
     if (tile >= total_tiles) return;
+    // compact twiddle table omega_R^i (i < R/2) in shared memory, after the tile buffer(s): every generic-round
+    // twiddle of this CTA's whole life comes from here (LDS latency) instead of the L1/L2 path
+    uint2* stw = reinterpret_cast<uint2*>(smv_all + (DB ? 2 : 1) * T::CHUNKS);
+    if constexpr (T::TW_BYTES > 0) {
+        for (uint32_t i = tid; i < (uint32_t)(R / 2); i += NT) stw[i] = __ldg(&p.tw[i << (LOG_TW - LR)]);
+    }
     if (DB) {
         const uint32_t bz = tile / tiles_x, tx = tile - bz * tiles_x;
         load_tile_v4<LR, LC>(smv_all, p.in + (size_t)bz * p.in_batch_stride, p, tx * C);
@@ -383,27 +396,28 @@ __global__ void __launch_bounds__(V4<LR, LC>::NT) ntt_pass_v4_kernel(const PassP
         }
 
         // ---- radix-16 DIT rounds, strides 1, 16, 256
-        if constexpr (T::G1 > 0) dit_round_v4<LR, LC, 0, T::G1>(smv, p);
+        if constexpr (T::G1 > 0) dit_round_v4<LR, LC, 0, T::G1>(smv, stw, p);
         if constexpr (T::G2 > 0) {
             __syncthreads();
-            dit_round_v4<LR, LC, 4, T::G2>(smv, p);
+            dit_round_v4<LR, LC, 4, T::G2>(smv, stw, p);
         }
         if constexpr (T::G3 > 0) {
             __syncthreads();
-            dit_round_v4<LR, LC, 8, T::G3>(smv, p);
+            dit_round_v4<LR, LC, 8, T::G3>(smv, stw, p);
         }
         __syncthreads();
 
         // ---- epilogue + store
+        const uint32_t epi_mode = p.epi_mode;
         if (p.log_pfull >= 2) {
-            switch (p.epi_mode) {
+            switch (epi_mode) {
                 case EPI_TWIDDLE: store_rows_v4<LR, LC, EPI_TWIDDLE>(smv, out, p, col0); break;
                 case EPI_OUTIDX: store_rows_v4<LR, LC, EPI_OUTIDX>(smv, out, p, col0); break;
                 case EPI_CONST: store_rows_v4<LR, LC, EPI_CONST>(smv, out, p, col0); break;
                 default: store_rows_v4<LR, LC, EPI_NONE>(smv, out, p, col0); break;
             }
         } else {
-            switch (p.epi_mode) {
+            switch (epi_mode) {
                 case EPI_TWIDDLE: store_cols_v4<LR, LC, EPI_TWIDDLE>(smv, out, p, col0); break;
                 case EPI_CONST: store_cols_v4<LR, LC, EPI_CONST>(smv, out, p, col0); break;
                 default: store_cols_v4<LR, LC, EPI_NONE>(smv, out, p, col0); break;
@@ -417,7 +431,7 @@ template <int LR, int LC>
 void launch_pass_v4(const PassParams& p, dim3 grid, cudaStream_t s) {
     using T = V4<LR, LC>;
     constexpr bool DB = (2 * T::SMEM <= 96 * 1024);  // double buffering only where >= 2 CTAs still fit per SM
-    constexpr size_t smem = DB ? 2 * T::SMEM : T::SMEM;
+    constexpr size_t smem = (DB ? 2 * T::SMEM : T::SMEM) + T::TW_BYTES;
     static int ctas_per_sm[64] = {};
     static int n_sm[64] = {};
     int dev = 0;
