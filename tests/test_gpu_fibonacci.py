@@ -1,0 +1,57 @@
+"""Config 1: Fibonacci AIR proofs assembled from GPU-computed pieces are byte-identical to the CPU oracle's, the
+oracle verifier (src/verifier.rs restated) accepts them, and the reference's tamper cases are rejected."""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import fibonacci as F
+
+
+def test_oracle_prover_and_verifier_cpu():
+    """test_fibonacci / test_verify_valid_proof at the reference's size (trace_len 64, src/fibonacci.rs:423,
+    src/verifier.rs:290), literal Lagrange interpolation vs the INTT shortcut, and the proof shape of Appendix A."""
+    tr = F.fibonacci_trace(64)
+    rnd = F.proof_randomness(64)
+    p = F.generate_proof(tr, *rnd)
+    assert F.verify(p)
+    assert len(p["fri_commitments"]) == 9 and len(p["fri_final_layer"]) == 8 and len(p["query_proofs"]) == 44
+    assert F.serialize_proof(p) == F.serialize_proof(F.generate_proof(tr, *rnd, interpolate="intt"))
+    other = F.generate_proof(tr, *F.proof_randomness(64, seed=99))
+    assert F.serialize_proof(other) != F.serialize_proof(p)  # src/verifier.rs:304-312: blinding changes the proof
+    bad_trace = tr.copy()
+    bad_trace[10] = (bad_trace[10] + 1) % F.P
+    with pytest.raises(AssertionError):  # src/fibonacci.rs:433-455: a corrupted trace fails the OOD check
+        F.generate_proof(bad_trace, *rnd)
+
+
+def _tamper_cases(p):  # src/verifier.rs:314-380
+    a = copy.deepcopy(p); a["t_z"] = (a["t_z"] + 1) % F.P; yield a
+    a = copy.deepcopy(p); a["q_z"] = (a["q_z"] + 1) % F.P; yield a
+    a = copy.deepcopy(p); a["trace_commitment"] = bytes(32); yield a
+    a = copy.deepcopy(p); a["fri_final_layer"][0] = (a["fri_final_layer"][0] + 1) % F.P; yield a
+    a = copy.deepcopy(p); a["query_proofs"][0]["deep_opening"]["value"] = (a["query_proofs"][0]["deep_opening"]["value"] + 1) % F.P; yield a
+    a = copy.deepcopy(p); a["fri_commitments"] = a["fri_commitments"][:-1]; yield a
+    a = copy.deepcopy(p); a["query_proofs"][3]["fri_openings"][0][0]["value"] ^= 1; yield a
+
+
+def test_verifier_rejects_tampering_cpu():
+    p = F.generate_proof(F.fibonacci_trace(64), *F.proof_randomness(64))
+    for bad in _tamper_cases(p):
+        assert not F.verify(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("trace_len", [64, 1 << 10])
+def test_gpu_proof_is_byte_identical_and_verifies(trace_len):
+    from toyni_b200 import prover
+    tr = F.fibonacci_trace(trace_len)
+    rnd = F.proof_randomness(trace_len)
+    ref = F.generate_proof(tr, *rnd, interpolate="lagrange" if trace_len == 64 else "intt")
+    got = prover.generate_proof(tr, *rnd)
+    assert F.serialize_proof(got) == F.serialize_proof(ref)
+    assert F.verify(got)
+    if trace_len == 1 << 10:  # shape of BASELINE config 1
+        assert got["lde_size"] == 32768 and len(got["fri_commitments"]) == 12 and len(got["fri_final_layer"]) == 16
+    for bad in _tamper_cases(got):
+        assert not F.verify(bad)
