@@ -131,7 +131,8 @@ int bb_merkle_open_device(const uint8_t* d_nodes, size_t nleaves, size_t index, 
  *   challenge  : called once per fold with the root just committed (absorb) and must return
  *                beta (squeeze) — limbs values; it is the host transcript (src/transcript.rs).
  *                When NULL, betas_in supplies limbs values per fold (fold-only benchmarking).
- *   d_layers   : receives all layers back to back (n + n/2 + ... + final_size values)
+ *   d_layers   : receives the folded layers 1, 2, ... back to back (n/2 + n/4 + ... + final_size values);
+ *                layer 0 stays in d_layer0
  *   d_nodes    : receives the trees back to back (bb_merkle_node_count per layer); NULL skips hashing
  *   roots_out  : 32 bytes per layer (host); NULL if d_nodes is NULL
  * Returns the number of folds through *folds_out. */

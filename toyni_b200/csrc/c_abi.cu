@@ -309,9 +309,8 @@ int bb_fri_commit_device(const uint32_t* d_layer0, size_t n, uint32_t shift, siz
     if (!challenge && !betas_in && n > final_size) return note((int)cudaErrorInvalidValue);
     if (challenge && !d_nodes) return note((int)cudaErrorInvalidValue);  // a transcript needs roots
     cudaStream_t s = cur_stream();
-    uint32_t* cur = d_layers;
-    if (d_layer0 != d_layers)
-        CK(cudaMemcpyAsync(d_layers, d_layer0, n * (size_t)limbs * 4, cudaMemcpyDeviceToDevice, s));
+    const uint32_t* cur = d_layer0;  // layer 0 stays where the caller has it; d_layers receives layers 1, 2, ...
+    uint32_t* next = d_layers;
     size_t cur_n = n, folds = 0;
     uint32_t x0 = shift, log_m = log2_of(n);
     const uint8_t* salt_ptr = d_salts;
@@ -333,7 +332,6 @@ int bb_fri_commit_device(const uint32_t* d_layer0, size_t n, uint32_t shift, siz
             challenge(user, root, (uint32_t)folds, beta);  // absorb(root) happened for this root; squeeze beta (:223)
         else
             memcpy(beta, betas_in + (size_t)limbs * folds, sizeof(uint32_t) * (size_t)limbs);
-        uint32_t* next = cur + cur_n * (size_t)limbs;
         CK(fri_fold_coset(cur, next, cur_n, limbs, (int)log_m, x0, beta, 1, 0, s));  // :225
         g_launches++;
         x0 = bb::mul(x0, x0);  // :228-231: x <- x^2
@@ -352,6 +350,7 @@ int bb_fri_commit_device(const uint32_t* d_layer0, size_t n, uint32_t shift, siz
             node_ptr += 32 * merkle_node_count(cur_n);
         }
         cur = next;
+        next += cur_n * (size_t)limbs;
     }
     if (folds_out) *folds_out = folds;
     return 0;

@@ -24,24 +24,67 @@ __global__ void __launch_bounds__(256) fold_base_kernel(const uint32_t* __restri
     out[i] = add(halve(add(a, b)), monty_mul(sub(a, b), tw));
 }
 
-__global__ void __launch_bounds__(256) fold_ext_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t half,
-                                                       PowTable winv, FoldIdx fi, Ext c_m) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= half) return;
-    uint4 av = in[i], bv = in[i + half];
-    Ext a{{av.x, av.y, av.z, av.w}}, b{{bv.x, bv.y, bv.z, bv.w}};
-    uint32_t tw = pow_lookup(winv, ((uint32_t)i * fi.idx_mul + fi.idx_add) << fi.shift);
-    Ext g;  // Montgomery form of (beta/2 * x0^-1) * omega^-i
+// Ext * (Ext constant): out_k = sum_j d_j * C[k][j] with C the 4x4 multiplication matrix of the constant
+// (W-scaled where X^4 wraps, src/ext.rs:186-189), entries in Montgomery form.  The four 62-bit products of a row are
+// accumulated in 64 bits (4 p^2 < 2^64) and reduced ONCE: 4 IMAD.WIDE + 1 Montgomery reduction per limb instead of
+// 4-5 full modular multiplications.
+struct ExtMat {
+    uint32_t m[4][4];
+};
+
+__device__ __forceinline__ uint32_t redc64(unsigned long long t) {  // t < 2^64 -> t * 2^-32 mod p, canonical
+    const uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
+    const uint32_t mm = lo * P_INV;
+    const uint32_t u = __umulhi(mm, P);
+    uint32_t r = hi - u;              // true value in (-p, 2p): hi < 2^32 < 2.14 p
+    if (hi < u) r += P;               // negative -> + p  (then in [0, p))
+    return min(r, r - P);             // [0, 2p) -> [0, p)
+}
+
+__device__ __forceinline__ Ext ext_mul_const(const Ext& d, const ExtMat& c) {
+    Ext r;
 #pragma unroll
-    for (int k = 0; k < 4; k++) g.c[k] = monty_mul(c_m.c[k], tw);
-    Ext s = ext_add(a, b), d = ext_sub(a, b);
-    Ext t = ext_mul_monty(d, g);
-    uint4 r;
-    r.x = add(halve(s.c[0]), t.c[0]);
-    r.y = add(halve(s.c[1]), t.c[1]);
-    r.z = add(halve(s.c[2]), t.c[2]);
-    r.w = add(halve(s.c[3]), t.c[3]);
-    out[i] = r;
+    for (int k = 0; k < 4; k++) {
+        unsigned long long acc = (unsigned long long)d.c[0] * c.m[k][0];
+        acc += (unsigned long long)d.c[1] * c.m[k][1];
+        acc += (unsigned long long)d.c[2] * c.m[k][2];
+        acc += (unsigned long long)d.c[3] * c.m[k][3];
+        r.c[k] = redc64(acc);
+    }
+    return r;
+}
+
+// PER_THREAD outputs per thread: more independent 16-byte loads in flight per warp
+template <int PER_THREAD>
+__global__ void __launch_bounds__(256) fold_ext_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t half,
+                                                       PowTable winv, FoldIdx fi, ExtMat cm) {
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x) * PER_THREAD + threadIdx.x;
+    uint4 av[PER_THREAD], bv[PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < PER_THREAD; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < half) {
+            av[u] = in[i];
+            bv[u] = in[i + half];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < PER_THREAD; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i >= half) continue;
+        Ext a{{av[u].x, av[u].y, av[u].z, av[u].w}}, b{{bv[u].x, bv[u].y, bv[u].z, bv[u].w}};
+        const uint32_t tw = pow_lookup(winv, ((uint32_t)i * fi.idx_mul + fi.idx_add) << fi.shift);  // omega^-i, Montgomery form
+        Ext s = ext_add(a, b), d = ext_sub(a, b);
+#pragma unroll
+        for (int k = 0; k < 4; k++) d.c[k] = monty_mul(d.c[k], tw);  // (a-b) * omega^-i, plain
+        const Ext t = ext_mul_const(d, cm);                             // * (beta/2 * x0^-1)
+        uint4 r;
+        r.x = add(halve(s.c[0]), t.c[0]);
+        r.y = add(halve(s.c[1]), t.c[1]);
+        r.z = add(halve(s.c[2]), t.c[2]);
+        r.w = add(halve(s.c[3]), t.c[3]);
+        out[i] = r;
+    }
 }
 
 // general evaluation points: x^-1 by Fermat, exactly as src/babybear.rs:111-114 (but in Montgomery form)
@@ -101,9 +144,17 @@ int fri_fold_coset(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int li
     if (limbs == 1) {
         fold_base_kernel<<<blocks_for(half), 256, 0, s>>>(d_in, d_out, half, winv, fi, to_monty(bb::mul(hx, beta[0])));
     } else {
-        Ext c;
-        for (int k = 0; k < 4; k++) c.c[k] = to_monty(bb::mul(hx, beta[k]));
-        fold_ext_kernel<<<blocks_for(half), 256, 0, s>>>((const uint4*)d_in, (uint4*)d_out, half, winv, fi, c);
+        // multiplication matrix of c = beta * (1/2 x0^-1): (d*c)_k = sum_j d_j c_(k-j), wrapped terms times W = 11
+        uint32_t c[4];
+        for (int k = 0; k < 4; k++) c[k] = bb::mul(hx, beta[k]);
+        ExtMat cm;
+        for (int k = 0; k < 4; k++)
+            for (int j = 0; j < 4; j++) {
+                uint32_t v = (k >= j) ? c[k - j] : bb::mul(EXT_W, c[k - j + 4]);
+                cm.m[k][j] = to_monty(v);
+            }
+        constexpr int PT = 2;
+        fold_ext_kernel<PT><<<(unsigned)((half + 256 * PT - 1) / (256 * PT)), 256, 0, s>>>((const uint4*)d_in, (uint4*)d_out, half, winv, fi, cm);
     }
     return (int)cudaGetLastError();
 }

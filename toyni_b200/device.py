@@ -157,7 +157,7 @@ def fri_commit(layer0, shift, final_size, salts=None, challenge=None, betas=None
         if m <= final_size:
             break
         m //= 2
-    total = sum(sizes)
+    total = max(1, sum(sizes[1:]))  # folded layers only; layer 0 stays in the caller's tensor
     dev = layer0.device
     layers = torch.empty((total, 4) if limbs == 4 else (total,), dtype=torch.int32, device=dev)
     nodes = roots = None
@@ -183,9 +183,12 @@ def fri_commit(layer0, shift, final_size, salts=None, challenge=None, betas=None
                                      None if nodes is None else C.c_void_p(nodes.data_ptr()),
                                      None if roots is None else roots.ctypes.data, C.byref(folds)), "bb_fri_commit_device")
     out_layers, out_nodes, off, noff = [], [], 0, 0
-    for s in sizes:
-        out_layers.append(layers[off:off + s])
-        off += s
+    for k, s in enumerate(sizes):
+        if k == 0:
+            out_layers.append(layer0)
+        else:
+            out_layers.append(layers[off:off + s])
+            off += s
         if nodes is not None:
             c = merkle_node_count(s)
             out_nodes.append(nodes[noff:noff + c])
