@@ -254,6 +254,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ntt24", choices=["ntt24", "fourstep27"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="fourstep27: fused peer stores or NCCL all-to-all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

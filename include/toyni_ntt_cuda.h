@@ -84,6 +84,17 @@ int bb_ntt_ext_device(uint32_t* d_data, uint32_t log_n, int dir);
  * The transpose between the two halves is an all-to-all owned by the caller (toyni_b200/multigpu.py, NCCL). */
 int bb_ntt_columns_device(uint32_t* d_block, uint32_t log_n1, size_t cols, int dir);
 int bb_fourstep_twiddle_device(uint32_t* d_block, uint32_t log_n, uint32_t log_n1, size_t cols, size_t col_offset, int dir);
+/* Fused form: the column transforms of this rank's block, with the twiddle AND the transpose folded into the last
+ * NTT pass.  Row k1 is stored, already multiplied by w_n^(j2*k1), straight into peer_bufs[k1 / (n1/nranks)] at
+ * [k1 mod (n1/nranks)][rank*cols + c] (row stride n2): peer_bufs[r] is rank r's receive buffer of (n1/nranks) x n2
+ * words — this rank's own allocation for r == rank, a CUDA-IPC mapping (stores over NVLink) otherwise.  The caller
+ * synchronises the ranks before (buffers free) and after (stores landed); no NCCL call, no re-layout pass. */
+int bb_ntt_columns_scatter_device(uint32_t* d_block, uint32_t log_n, uint32_t log_n1, size_t cols, int dir,
+                                  void* const* peer_bufs, uint32_t nranks, uint32_t rank);
+/* CUDA IPC plumbing for the peer buffers (one process per GPU): 64-byte handles, exchanged by the caller. */
+int bb_ipc_get_handle(const void* d_ptr, uint8_t handle_out[64]);
+int bb_ipc_open_handle(const uint8_t handle[64], void** d_ptr_out);
+int bb_ipc_close_handle(void* d_ptr);
 
 /* BabyBearDomain::fft on a coset (src/math/domain.rs:107-123,154-162): zero-pad/truncate the
  * n_coeffs coefficients to 2^log_size, multiply by shift^i, forward NTT.  Fused into the first

@@ -250,3 +250,22 @@ def test_ntt_2_24_against_oracle_checksum(D):
     ref = O.ntt(x, threads=os.cpu_count() or 1)
     got = D.to_host(D.ntt_(D.to_device(x)))
     assert np.array_equal(got, ref)
+
+
+# ------------------------------------------------------------------ four-step building blocks (multi-GPU layer)
+@pytest.mark.parametrize("log_n", [10, 16, 21])
+def test_fourstep_paths_on_one_gpu(D, log_n):
+    """The sharded four-step NTT with world = 1: both the NCCL-shaped path (twiddle kernel + row transforms) and
+    the fused path (twiddle + transpose inside the last column pass, stores into the receive buffer) must equal
+    the 1-D transform.  With world > 1 the same code runs under torchrun (tools/mg_check.py)."""
+    from toyni_b200 import multigpu as MG
+    n = 1 << log_n
+    x = O.random_field(n, seed=log_n)
+    for inv in (False, True):
+        ref = O.intt(x, threads=4) if inv else O.ntt(x, threads=4)
+        out = MG.fourstep_ntt_cuda(D.to_device(MG.fourstep_scatter(x, 0, 1)), log_n, 0, 1, inverse=inv)
+        assert np.array_equal(MG.fourstep_gather([D.to_host(out)], log_n), ref)
+        fs = MG.FourStepFused(log_n, 0, 1)
+        out = fs.run(D.to_device(MG.fourstep_scatter(x, 0, 1)), inverse=inv)
+        assert np.array_equal(MG.fourstep_gather([D.to_host(out)], log_n), ref)
+        fs.close()

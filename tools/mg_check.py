@@ -23,6 +23,21 @@ for log_n in (12, 16, 20):
         good = np.array_equal(D.to_host(out), want)
         ok &= good
         if rank == 0: print(f"fourstep log_n={log_n} inv={inv} world={world}: {'OK' if good else 'FAIL'}", flush=True)
+# fused exchange (peer stores over NVLink inside the NTT pass)
+for log_n in (12, 16, 20, 22):
+    n = 1 << log_n
+    x = O.random_field(n, seed=100 + log_n)
+    fs = MG.FourStepFused(log_n, rank, world)
+    for inv in (False, True):
+        blk = D.to_device(MG.fourstep_scatter(x, rank, world))
+        out = fs.run(blk, inverse=inv)
+        n1, n2 = MG.fourstep_split(log_n, world)
+        k1 = np.arange(rank * n1 // world, (rank + 1) * n1 // world)
+        want = (O.intt(x, threads=4) if inv else O.ntt(x, threads=4)).reshape(n2, n1)[:, k1].T
+        good = np.array_equal(D.to_host(out), want)
+        ok &= good
+        if rank == 0: print(f"fused fourstep log_n={log_n} inv={inv} world={world}: {'OK' if good else 'FAIL'}", flush=True)
+    fs.close()
 # cyclic fold chain
 m_log = 14
 ee = O.random_field(4 << m_log, seed=3).reshape(1 << m_log, 4)

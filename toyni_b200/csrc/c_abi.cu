@@ -183,7 +183,7 @@ int bb_widen_u32_to_u64(const uint32_t* d_src, uint64_t* d_dst, size_t count) {
 }
 
 static int run_ntt(const uint32_t* in, uint32_t* out, uint32_t log_n, int log_inner, size_t n_in, size_t batch, int dir,
-                   uint32_t shift) {
+                   uint32_t shift, const FourStepScatter* scatter = nullptr) {
     if (log_n > (uint32_t)MAX_LOG_N || (dir != 0 && dir != 1)) return note((int)cudaErrorInvalidValue);
     if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
     NttDesc d{};
@@ -196,6 +196,7 @@ static int run_ntt(const uint32_t* in, uint32_t* out, uint32_t log_n, int log_in
     d.batch = batch;
     d.batch_stride_in = d.batch_stride_out = ((size_t)1 << log_n) << log_inner;
     d.coset_shift = shift;
+    d.scatter = scatter;
     CK(ntt_execute(d, cur_stream()));
     g_launches += (unsigned)ntt_plan_for((int)log_n, log_inner, batch).npass;
     return 0;
@@ -220,6 +221,33 @@ int bb_fourstep_twiddle_device(uint32_t* d_block, uint32_t log_n, uint32_t log_n
     g_launches++;
     return 0;
 }
+
+int bb_ntt_columns_scatter_device(uint32_t* d_block, uint32_t log_n, uint32_t log_n1, size_t cols, int dir,
+                                  void* const* peer_bufs, uint32_t nranks, uint32_t rank) {
+    if (!is_pow2(cols) || !is_pow2(nranks) || nranks > 8 || rank >= nranks || log_n1 >= log_n || !peer_bufs)
+        return note((int)cudaErrorInvalidValue);
+    FourStepScatter fs{};
+    for (uint32_t r = 0; r < nranks; r++) fs.peer[r] = (uint32_t*)peer_bufs[r];
+    fs.nranks = (int)nranks;
+    fs.rank = (int)rank;
+    fs.log_n = (int)log_n;
+    fs.dst_row_stride = (size_t)1 << (log_n - log_n1);  // n2
+    fs.col_offset = (size_t)rank * cols;
+    return run_ntt(d_block, d_block, log_n1, (int)log2_of(cols), (size_t)1 << log_n1, 1, dir, 1, &fs);
+}
+int bb_ipc_get_handle(const void* d_ptr, uint8_t handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+int bb_ipc_open_handle(const uint8_t handle[64], void** d_ptr_out) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    return note((int)cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+}
+int bb_ipc_close_handle(void* d_ptr) { return note((int)cudaIpcCloseMemHandle(d_ptr)); }
 
 int bb_coset_fft_device(const uint32_t* d_coeffs, size_t n_coeffs, uint32_t log_size, uint32_t shift, int limbs,
                         uint32_t* d_out) {

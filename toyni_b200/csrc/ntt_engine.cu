@@ -300,6 +300,15 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
         if (rc) return rc;
     }
 
+    PowTable fs_tab{};
+    if (d.scatter) {
+        if (coset || d.batch != 1 || d.log_inner < 4) return (int)cudaErrorInvalidValue;
+        uint32_t wn = root_of_unity(d.scatter->log_n);
+        if (inv) wn = bb::inv(wn);
+        rc = pow_table_get(*st, wn, d.scatter->log_n, 1u, &fs_tab);
+        if (rc) return rc;
+    }
+
     uint32_t* scratch = nullptr;
     if (pl.npass > 1) {
         rc = scratch_get(*st, n * inner * d.batch, &scratch);
@@ -375,6 +384,15 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
             p.epi = first ? tw_first : tw_rest;
             p.epi_shift = (uint32_t)log_p;
             p.epi_unscale = (first && inv && !coset) ? to_monty((uint32_t)(n % P)) : R_MOD_P;
+        } else if (d.scatter) {
+            p.epi_mode = EPI_FOURSTEP;
+            p.epi = fs_tab;
+            p.epi_const = (inv && pl.npass == 1) ? to_monty(n_inv) : 0u;
+            for (int r = 0; r < 8; r++) p.fs_peer[r] = d.scatter->peer[r < d.scatter->nranks ? r : 0];
+            p.fs_log_rows_per_rank = (uint32_t)(d.log_n - ceil_log2((size_t)d.scatter->nranks));
+            p.fs_dst_row_stride = (uint32_t)d.scatter->dst_row_stride;
+            p.fs_dst_col = (uint32_t)d.scatter->col_offset;
+            p.fs_col_offset = (uint32_t)d.scatter->col_offset;
         } else if (coset && inv) {
             p.epi_mode = EPI_OUTIDX;
             p.epi = coset_tab;
@@ -389,6 +407,7 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
         const bool aligned = ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) && (src_bs % 4 == 0) && (dst_bs % 4 == 0);
         if (!transposed && lc >= 2 && aligned && p.log_pfull != 1 && (p.ncols & ((1u << lc) - 1u)) == 0 && !g_force_scalar)
             fn = pass_launcher_v4(lr, lc);
+        if (!fn && p.epi_mode == EPI_FOURSTEP) return (int)cudaErrorInvalidConfiguration;
         if (!fn) fn = pass_launcher(lr, lc);
         if (!fn) return (int)cudaErrorInvalidConfiguration;
         fn(p, grid, stream);

@@ -19,6 +19,15 @@ struct NttPlan {
     int lc[3];
 };
 
+// Sharded four-step NTT: fuse the inter-half twiddle and the transpose into the last pass of the column transforms.
+struct FourStepScatter {
+    uint32_t* peer[8];        // receive buffer of every rank (own buffer for this rank; peer mappings otherwise)
+    int nranks, rank;
+    int log_n;                // full transform length
+    size_t dst_row_stride;    // n2
+    size_t col_offset;        // first global column of this rank's block (= rank * cols)
+};
+
 struct NttDesc {
     int log_n;              // transform length 2^log_n
     int log_inner;          // interleaved columns per element (0 plain, 2 for AoS Ext)
@@ -30,6 +39,7 @@ struct NttDesc {
     size_t batch_stride_in;   // in elements*inner (u32 units)
     size_t batch_stride_out;
     uint32_t coset_shift;   // 0 or 1: none.  forward: x[i] *= s^i first; inverse: y[k] *= s^-k afterwards
+    const FourStepScatter* scatter;  // non-null: column transforms of a four-step NTT (log_inner = log2 cols)
 };
 
 // All functions return cudaError_t as int (0 = success) and never synchronise the stream.

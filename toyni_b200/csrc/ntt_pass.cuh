@@ -26,7 +26,7 @@ namespace bb {
 constexpr int LOG_TW = 12;  // the master Shoup twiddle table covers omega_4096 (largest in-tile transform)
 
 enum : uint32_t { PRO_NONE = 0, PRO_INIDX = 1 };
-enum : uint32_t { EPI_NONE = 0, EPI_TWIDDLE = 1, EPI_OUTIDX = 2, EPI_CONST = 3 };
+enum : uint32_t { EPI_NONE = 0, EPI_TWIDDLE = 1, EPI_OUTIDX = 2, EPI_CONST = 3, EPI_FOURSTEP = 4 };
 
 // g^t = hi[t >> lo_bits] * lo[t & mask]; entries are Shoup pairs (w, floor(w 2^32 / p)) of plain values
 struct PowTable {
@@ -53,6 +53,14 @@ struct PassParams {
     uint32_t epi_const;  // Montgomery-form constant for EPI_CONST
     uint32_t epi_unscale;  // Montgomery form of the inverse of the constant factor folded into epi.lo (R mod p if none)
     uint32_t epi_shift;  // EPI_TWIDDLE exponent = (j*e) << epi_shift
+    // EPI_FOURSTEP (last pass of the column transforms of a sharded four-step NTT): multiply element (k1, c) by
+    // w_n^((fs_col_offset + c) * k1) (table `epi`) and store row k1 into the buffer of the rank that owns it —
+    // a peer pointer over NVLink for another rank — at [k1 mod rows_per_rank][fs_dst_col + c]
+    uint32_t* fs_peer[8];
+    uint32_t fs_log_rows_per_rank;
+    uint32_t fs_dst_row_stride;
+    uint32_t fs_dst_col;
+    uint32_t fs_col_offset;
 };
 
 __host__ __device__ constexpr int rpad(int r) { return r + (r >> 4); }

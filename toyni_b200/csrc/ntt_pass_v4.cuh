@@ -225,6 +225,34 @@ BB_D void store_rows_v4(const uint4* __restrict__ smv, uint32_t* __restrict__ ou
     }
 }
 
+// ---- last pass of the column transforms of a sharded four-step NTT: inter-half twiddle + transpose in one go.
+//      Row k1 of the local block belongs to rank k1 / rows_per_rank; it is written straight into that rank's
+//      receive buffer (a peer mapping, i.e. stores that travel over NVLink) at the column range of this rank, so the
+//      all-to-all exchange and the re-layout pass disappear into the NTT pass's own stores.
+template <int LR, int LC>
+BB_D void store_fourstep_v4(const uint4* __restrict__ smv, const PassParams& p, uint32_t col0) {
+    using T = V4<LR, LC>;
+    constexpr int R = T::R, CV = T::CV, LCV = T::LCV, NT = T::NT;
+    const uint32_t log_p = p.log_pfull - p.log_inner;
+    const uint32_t low_p = col0 >> p.log_inner, c0 = col0 & ((1u << p.log_inner) - 1u);
+    const uint32_t rpr_mask = (1u << p.fs_log_rows_per_rank) - 1u;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < R * CV; i += NT) {
+        const uint32_t cv = i & (CV - 1), e = i >> LCV;
+        uint4 v = smv[T::chunk(e, cv)];
+        const uint32_t k1 = (e << log_p) + low_p, c = c0 + 4u * cv;
+        uint32_t tw = pow_lookup(p.epi, (p.fs_col_offset + c) * k1);  // geometric in c, ratio w^k1
+        const uint32_t g = pow_lookup(p.epi, k1);
+        if (p.epi_const) tw = monty_mul(tw, p.epi_const);                // n1^-1 of a single-pass inverse
+        v.x = monty_mul(v.x, tw); tw = monty_mul(tw, g);
+        v.y = monty_mul(v.y, tw); tw = monty_mul(tw, g);
+        v.z = monty_mul(v.z, tw); tw = monty_mul(tw, g);
+        v.w = monty_mul(v.w, tw);
+        uint32_t* dst = p.fs_peer[k1 >> p.fs_log_rows_per_rank] + (size_t)(k1 & rpr_mask) * p.fs_dst_row_stride + p.fs_dst_col + c;
+        *reinterpret_cast<uint4*>(dst) = v;
+    }
+}
+
 // ---- epilogue + store for the first pass of a plain vector (pfull == 1): column col becomes the contiguous run
 //      out[col*R + e]; lanes walk e, so each of the four scalar stores of a chunk is coalesced.  The inter-pass
 //      twiddle w^(col*e) is generated on chip: for a fixed row e it is a geometric sequence in col, so a thread
@@ -409,7 +437,9 @@ __global__ void __launch_bounds__(V4<LR, LC>::NT) ntt_pass_v4_kernel(const PassP
 
         // ---- epilogue + store
         const uint32_t epi_mode = p.epi_mode;
-        if (p.log_pfull >= 2) {
+        if (epi_mode == EPI_FOURSTEP) {
+            store_fourstep_v4<LR, LC>(smv, p, col0);
+        } else if (p.log_pfull >= 2) {
             switch (epi_mode) {
                 case EPI_TWIDDLE: store_rows_v4<LR, LC, EPI_TWIDDLE>(smv, out, p, col0); break;
                 case EPI_OUTIDX: store_rows_v4<LR, LC, EPI_OUTIDX>(smv, out, p, col0); break;

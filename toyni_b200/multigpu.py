@@ -119,6 +119,95 @@ def fourstep_ntt_cuda(block, log_n, rank, world, inverse=False):
     return ntt_batch_(rows, inverse)
 
 
+class _RawCudaBuffer:
+    """A cudaMalloc'ed buffer (not from torch's caching allocator, so that CUDA IPC maps exactly this allocation)
+    exposed through __cuda_array_interface__ so torch can view it."""
+
+    def __init__(self, nwords):
+        import ctypes as C
+
+        from .lib import check, lib
+        self.nwords = nwords
+        self.ptr = C.c_void_p()
+        check(lib().bb_dev_alloc(C.byref(self.ptr), nwords * 4), "bb_dev_alloc")
+        self.__cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i4", "data": (self.ptr.value, False), "version": 2}
+
+    def tensor(self, shape):
+        return torch.as_tensor(self, device="cuda").view(*shape)
+
+    def free(self):
+        from .lib import lib
+        if self.ptr:
+            lib().bb_dev_free(self.ptr)
+            self.ptr = None
+
+
+class FourStepFused:
+    """One 2^log_n NTT over `world` GPUs with the exchange fused into the compute: the last pass of the column
+    transforms multiplies by the inter-half twiddle and stores every row directly into the receive buffer of the
+    rank that owns it (CUDA-IPC peer mappings: the stores travel over NVLink / NVSwitch), already in the layout the
+    row transforms read.  Compared with `fourstep_ntt_cuda` this removes the twiddle pass, the NCCL all-to-all and
+    the re-layout copy; torch.distributed is used only for the handle exchange and the two barriers."""
+
+    def __init__(self, log_n, rank, world):
+        import ctypes as C
+
+        from .lib import check, lib
+        self.log_n, self.rank, self.world = log_n, rank, world
+        self.n1, self.n2 = fourstep_split(log_n, world)
+        self.rw, self.cw = self.n1 // world, self.n2 // world
+        self.recv = _RawCudaBuffer(self.rw * self.n2)
+        handle = (C.c_uint8 * 64)()
+        check(lib().bb_ipc_get_handle(self.recv.ptr, handle), "bb_ipc_get_handle")
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        if world > 1:
+            allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+        else:
+            allh = [mine]
+        self.peers = (C.c_void_p * world)()
+        self._opened = []
+        for r in range(world):
+            if r == rank:
+                self.peers[r] = self.recv.ptr.value
+            else:
+                hb = (C.c_uint8 * 64)(*allh[r].cpu().tolist())
+                p = C.c_void_p()
+                check(lib().bb_ipc_open_handle(hb, C.byref(p)), "bb_ipc_open_handle")
+                self.peers[r] = p.value
+                self._opened.append(p)
+        self.out = self.recv.tensor((self.rw, self.n2))
+
+    def _barrier(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+
+    def run(self, block, inverse=False):
+        """block: int32 CUDA tensor (n1, n2/G), this rank's columns (destroyed).  Returns the (n1/G, n2) receive
+        buffer holding out[k1_local][k2] = X[k1 + n1*k2] (valid until the next run)."""
+        from .device import _bind_stream, _chk, ntt_batch_
+        from .lib import check, lib
+        assert tuple(block.shape) == (self.n1, self.cw)
+        _bind_stream()
+        self._barrier()  # every rank has finished reading its receive buffer from the previous transform
+        check(lib().bb_ntt_columns_scatter_device(_chk(block), self.log_n, self.n1.bit_length() - 1, self.cw,
+                                                  1 if inverse else 0, self.peers, self.world, self.rank),
+              "bb_ntt_columns_scatter_device")
+        self._barrier()  # all peer stores have landed
+        return ntt_batch_(self.out, inverse)
+
+    def close(self):
+        from .lib import lib
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        for p in self._opened:
+            lib().bb_ipc_close_handle(p)
+        self._opened = []
+        self.recv.free()
+
+
 def fold_chain_cuda(local, log_m, shift, betas, rank, world, until=16):
     """FRI fold chain on one cyclic shard (global indices rank, rank+G, ...), betas supplied up front.
     Returns the list of local layers.  No communication while the layer has at least 2*world values."""
@@ -153,15 +242,17 @@ def bench_fourstep(args, rank, world, dev, log_n=27):
             dist.barrier()
         torch.cuda.synchronize()
 
+    fused = FourStepFused(log_n, rank, world) if getattr(args, "exchange", "peer") == "peer" else None
+    run = (lambda b: fused.run(b)) if fused else (lambda b: fourstep_ntt_cuda(b, log_n, rank, world))
     for i in range(max(args.warmup, 3)):
-        fourstep_ntt_cuda(blocks[i % 2].clone(), log_n, rank, world)
+        run(blocks[i % 2].clone())
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     work = [blocks[i % 2].clone() for i in range(min(args.steps, 4))]
     barrier()
     e0.record()
     for i in range(args.steps):
-        fourstep_ntt_cuda(work[i % len(work)], log_n, rank, world)
+        run(work[i % len(work)])
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -176,6 +267,9 @@ def bench_fourstep(args, rank, world, dev, log_n=27):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"one forward 2^{log_n} NTT, four-step, column blocks over {world} GPUs",
+                       "exchange": "peer stores fused into the NTT pass (CUDA IPC over NVLink)" if fused else "NCCL all-to-all",
                        "n1": n1, "n2": n2, "nvlink_bytes_sent_per_gpu_per_step": sent,
                        "l2": "each rank's block is 2^27/G x 4 B (>= 64 MiB), rotated over buffers"},
         }), flush=True)
+    if fused:
+        fused.close()
