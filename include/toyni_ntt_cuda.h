@@ -91,6 +91,13 @@ int bb_fourstep_twiddle_device(uint32_t* d_block, uint32_t log_n, uint32_t log_n
  * synchronises the ranks before (buffers free) and after (stores landed); no NCCL call, no re-layout pass. */
 int bb_ntt_columns_scatter_device(uint32_t* d_block, uint32_t log_n, uint32_t log_n1, size_t cols, int dir,
                                   void* const* peer_bufs, uint32_t nranks, uint32_t rank);
+/* Device-side rendezvous for the fused path (no host synchronisation, no NCCL): every rank owns 8 flag words
+ * (one 128-byte line per writer).  signal: after this rank's scatter kernels (stream order), write `epoch` into
+ * every rank's flag line for this rank (d_peer_flags: DEVICE array of nranks pointers to the ranks' flag blocks).
+ * wait: spin until all nranks lines of this rank's own flag block reach `epoch`; a lost peer sets *d_err (device
+ * word) after ~2 s instead of hanging. */
+int bb_peer_signal_device(void* const* d_peer_flags, uint32_t nranks, uint32_t rank, uint32_t epoch);
+int bb_peer_wait_device(void* d_flags, uint32_t nranks, uint32_t epoch, void* d_err);
 /* CUDA IPC plumbing for the peer buffers (one process per GPU): 64-byte handles, exchanged by the caller. */
 int bb_ipc_get_handle(const void* d_ptr, uint8_t handle_out[64]);
 int bb_ipc_open_handle(const uint8_t handle[64], void** d_ptr_out);

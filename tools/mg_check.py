@@ -10,7 +10,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for log_n in (12, 16, 20):
+for log_n in (14, 16, 20):
     n = 1 << log_n
     x = O.random_field(n, seed=log_n)
     ref = O.ntt(x, threads=4)
@@ -24,11 +24,11 @@ for log_n in (12, 16, 20):
         ok &= good
         if rank == 0: print(f"fourstep log_n={log_n} inv={inv} world={world}: {'OK' if good else 'FAIL'}", flush=True)
 # fused exchange (peer stores over NVLink inside the NTT pass)
-for log_n in (12, 16, 20, 22):
+for log_n in (14, 16, 20, 22):
     n = 1 << log_n
     x = O.random_field(n, seed=100 + log_n)
     fs = MG.FourStepFused(log_n, rank, world)
-    for inv in (False, True):
+    for inv in (False, True, False):
         blk = D.to_device(MG.fourstep_scatter(x, rank, world))
         out = fs.run(blk, inverse=inv)
         n1, n2 = MG.fourstep_split(log_n, world)
@@ -37,6 +37,7 @@ for log_n in (12, 16, 20, 22):
         good = np.array_equal(D.to_host(out), want)
         ok &= good
         if rank == 0: print(f"fused fourstep log_n={log_n} inv={inv} world={world}: {'OK' if good else 'FAIL'}", flush=True)
+    fs.check_peers()
     fs.close()
 # cyclic fold chain
 m_log = 14

@@ -235,6 +235,16 @@ int bb_ntt_columns_scatter_device(uint32_t* d_block, uint32_t log_n, uint32_t lo
     fs.col_offset = (size_t)rank * cols;
     return run_ntt(d_block, d_block, log_n1, (int)log2_of(cols), (size_t)1 << log_n1, 1, dir, 1, &fs);
 }
+int bb_peer_signal_device(void* const* d_peer_flags, uint32_t nranks, uint32_t rank, uint32_t epoch) {
+    CK(peer_signal((uint32_t* const*)d_peer_flags, nranks, rank, epoch, cur_stream()));
+    g_launches++;
+    return 0;
+}
+int bb_peer_wait_device(void* d_flags, uint32_t nranks, uint32_t epoch, void* d_err) {
+    CK(peer_wait((uint32_t*)d_flags, nranks, epoch, (uint32_t*)d_err, cur_stream()));
+    g_launches++;
+    return 0;
+}
 int bb_ipc_get_handle(const void* d_ptr, uint8_t handle_out[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     cudaIpcMemHandle_t h;

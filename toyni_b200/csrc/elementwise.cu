@@ -37,4 +37,41 @@ int fourstep_twiddle(uint32_t* d, int log_n, int log_n1, size_t cols, size_t col
     return (int)cudaGetLastError();
 }
 
+// ---- device-side rendezvous between the ranks of one box (one process per GPU, flags in CUDA-IPC peer memory)
+// signal: tell every rank that this rank's stores of epoch `epoch` are done (runs after the scatter kernels in stream
+// order; the system-scope fence orders those peer stores before the flag).
+__global__ void peer_signal_kernel(uint32_t* const* peer_flags, uint32_t nranks, uint32_t rank, uint32_t epoch) {
+    if (threadIdx.x < nranks) {
+        __threadfence_system();
+        volatile uint32_t* f = peer_flags[threadIdx.x] + 32u * rank;  // one 128-byte line per writer
+        *f = epoch;
+    }
+}
+// wait: spin until every rank has signalled `epoch` into this rank's flags.  Each GPU runs its own waiter, the
+// writers run on OTHER GPUs, so nothing here depends on co-scheduling; a clock bound turns a lost peer into an error
+// word instead of a hang.
+__global__ void peer_wait_kernel(volatile uint32_t* flags, uint32_t nranks, uint32_t epoch, uint32_t* err) {
+    if (threadIdx.x < nranks) {
+        const long long t0 = clock64();
+        volatile uint32_t* f = flags + 32u * threadIdx.x;
+        while ((int32_t)(*f - epoch) < 0) {
+            if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
+                *err = 1u + threadIdx.x;
+                break;
+            }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+}
+
+int peer_signal(uint32_t* const* d_peer_flags, uint32_t nranks, uint32_t rank, uint32_t epoch, cudaStream_t s) {
+    peer_signal_kernel<<<1, 32, 0, s>>>(d_peer_flags, nranks, rank, epoch);
+    return (int)cudaGetLastError();
+}
+int peer_wait(uint32_t* d_flags, uint32_t nranks, uint32_t epoch, uint32_t* d_err, cudaStream_t s) {
+    peer_wait_kernel<<<1, 32, 0, s>>>(d_flags, nranks, epoch, d_err);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace bb

@@ -16,6 +16,9 @@ int fri_fold_xs(const uint32_t* d_in, const uint32_t* d_xs, uint32_t* d_out, siz
                 cudaStream_t s);
 // four-step NTT, step 2: d[k1][c] *= w_n^((col_offset + c) * k1) over a local block of 2^log_n1 rows x cols columns
 int fourstep_twiddle(uint32_t* d, int log_n, int log_n1, size_t cols, size_t col_offset, bool inverse, cudaStream_t s);
+// device-side rendezvous over peer-mapped flag words (d_peer_flags: device array of nranks pointers)
+int peer_signal(uint32_t* const* d_peer_flags, uint32_t nranks, uint32_t rank, uint32_t epoch, cudaStream_t s);
+int peer_wait(uint32_t* d_flags, uint32_t nranks, uint32_t epoch, uint32_t* d_err, cudaStream_t s);
 // cached g^t tables (shared with the NTT engine)
 int engine_pow_table(uint32_t g, int log_total, uint32_t scale, PowTable* out);
 }  // namespace bb

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "bb_fourstep_twiddle_device": ([C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_size_t, C.c_int], C.c_int),
     "bb_ntt_columns_scatter_device": ([C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.c_uint32,
                                        C.c_uint32], C.c_int),
+    "bb_peer_signal_device": ([C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32], C.c_int),
+    "bb_peer_wait_device": ([C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p], C.c_int),
     "bb_ipc_get_handle": ([C.c_void_p, C.c_void_p], C.c_int),
     "bb_ipc_open_handle": ([C.c_void_p, C.POINTER(C.c_void_p)], C.c_int),
     "bb_ipc_close_handle": ([C.c_void_p], C.c_int),

@@ -147,7 +147,11 @@ class FourStepFused:
     transforms multiplies by the inter-half twiddle and stores every row directly into the receive buffer of the
     rank that owns it (CUDA-IPC peer mappings: the stores travel over NVLink / NVSwitch), already in the layout the
     row transforms read.  Compared with `fourstep_ntt_cuda` this removes the twiddle pass, the NCCL all-to-all and
-    the re-layout copy; torch.distributed is used only for the handle exchange and the two barriers."""
+    the re-layout copy.  The ranks rendezvous on the device (flag words in peer memory, one signal + one wait kernel
+    per transform, receive buffers double buffered), so a transform involves no host synchronisation and no NCCL
+    call; torch.distributed is used once, to exchange the IPC handles."""
+
+    FLAG_WORDS = 512  # 8 lines of 32 words for the flags, then the error word
 
     def __init__(self, log_n, rank, world):
         import ctypes as C
@@ -156,46 +160,69 @@ class FourStepFused:
         self.log_n, self.rank, self.world = log_n, rank, world
         self.n1, self.n2 = fourstep_split(log_n, world)
         self.rw, self.cw = self.n1 // world, self.n2 // world
-        self.recv = _RawCudaBuffer(self.rw * self.n2)
+        self.buf_words = self.rw * self.n2
+        # one allocation per rank: [receive buffer 0][receive buffer 1][flags + error word]
+        self.mem = _RawCudaBuffer(2 * self.buf_words + self.FLAG_WORDS)
+        whole = self.mem.tensor((2 * self.buf_words + self.FLAG_WORDS,))
+        whole[2 * self.buf_words:].zero_()
+        torch.cuda.synchronize()
         handle = (C.c_uint8 * 64)()
-        check(lib().bb_ipc_get_handle(self.recv.ptr, handle), "bb_ipc_get_handle")
+        check(lib().bb_ipc_get_handle(self.mem.ptr, handle), "bb_ipc_get_handle")
         mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
         if world > 1:
             allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
             dist.all_gather(allh, mine)
         else:
             allh = [mine]
-        self.peers = (C.c_void_p * world)()
+        base = []
         self._opened = []
         for r in range(world):
             if r == rank:
-                self.peers[r] = self.recv.ptr.value
+                base.append(self.mem.ptr.value)
             else:
                 hb = (C.c_uint8 * 64)(*allh[r].cpu().tolist())
                 p = C.c_void_p()
                 check(lib().bb_ipc_open_handle(hb, C.byref(p)), "bb_ipc_open_handle")
-                self.peers[r] = p.value
+                base.append(p.value)
                 self._opened.append(p)
-        self.out = self.recv.tensor((self.rw, self.n2))
-
-    def _barrier(self):
-        torch.cuda.synchronize()
-        if self.world > 1:
-            dist.barrier()
+        self.peers = [(C.c_void_p * world)(*[b + 4 * k * self.buf_words for b in base]) for k in range(2)]
+        flag_ptrs = [b + 4 * 2 * self.buf_words for b in base]
+        self.d_peer_flags = torch.tensor(flag_ptrs, dtype=torch.int64, device="cuda")  # device array of pointers
+        self.flags_ptr = C.c_void_p(base[rank] + 4 * 2 * self.buf_words)
+        self.err_ptr = C.c_void_p(base[rank] + 4 * (2 * self.buf_words + 256))
+        self.err = whole[2 * self.buf_words + 256:2 * self.buf_words + 257]
+        self.out = [whole[k * self.buf_words:(k + 1) * self.buf_words].view(self.rw, self.n2) for k in range(2)]
+        self.epoch = 0
+        if world > 1:
+            dist.barrier()  # every rank has mapped every buffer and zeroed its flags
 
     def run(self, block, inverse=False):
         """block: int32 CUDA tensor (n1, n2/G), this rank's columns (destroyed).  Returns the (n1/G, n2) receive
-        buffer holding out[k1_local][k2] = X[k1 + n1*k2] (valid until the next run)."""
+        buffer holding out[k1_local][k2] = X[k1 + n1*k2]; it stays valid for the next transform (double buffered)."""
+        import ctypes as C
+
         from .device import _bind_stream, _chk, ntt_batch_
         from .lib import check, lib
         assert tuple(block.shape) == (self.n1, self.cw)
         _bind_stream()
-        self._barrier()  # every rank has finished reading its receive buffer from the previous transform
-        check(lib().bb_ntt_columns_scatter_device(_chk(block), self.log_n, self.n1.bit_length() - 1, self.cw,
-                                                  1 if inverse else 0, self.peers, self.world, self.rank),
+        self.epoch += 1
+        k = self.epoch & 1
+        L = lib()
+        # buffer k was last read by the row transforms of epoch-2; every rank finished those before it signalled
+        # epoch-1, and this rank has already waited for all epoch-1 signals: the peers' buffers are free
+        check(L.bb_ntt_columns_scatter_device(_chk(block), self.log_n, self.n1.bit_length() - 1, self.cw,
+                                              1 if inverse else 0, self.peers[k], self.world, self.rank),
               "bb_ntt_columns_scatter_device")
-        self._barrier()  # all peer stores have landed
-        return ntt_batch_(self.out, inverse)
+        check(L.bb_peer_signal_device(C.c_void_p(self.d_peer_flags.data_ptr()), self.world, self.rank, self.epoch),
+              "bb_peer_signal_device")
+        check(L.bb_peer_wait_device(self.flags_ptr, self.world, self.epoch, self.err_ptr), "bb_peer_wait_device")
+        return ntt_batch_(self.out[k], inverse)
+
+    def check_peers(self):
+        """Host-side check (synchronises): raises if a wait kernel gave up on a peer."""
+        e = int(self.err.item())
+        if e:
+            raise RuntimeError(f"four-step rendezvous timed out waiting for rank {e - 1}")
 
     def close(self):
         from .lib import lib
@@ -205,7 +232,7 @@ class FourStepFused:
         for p in self._opened:
             lib().bb_ipc_close_handle(p)
         self._opened = []
-        self.recv.free()
+        self.mem.free()
 
 
 def fold_chain_cuda(local, log_m, shift, betas, rank, world, until=16):
