@@ -370,16 +370,19 @@ int bb_fri_commit_device(const uint32_t* d_layer0, size_t n, uint32_t shift, siz
             challenge(user, root, (uint32_t)folds, beta);  // absorb(root) happened for this root; squeeze beta (:223)
         else
             memcpy(beta, betas_in + (size_t)limbs * folds, sizeof(uint32_t) * (size_t)limbs);
-        CK(fri_fold_coset(cur, next, cur_n, limbs, (int)log_m, x0, beta, 1, 0, s));  // :225
+        // fold (:225) and, when committing, the leaf level of the new layer's tree in the same kernel (:234-238:
+        // salted, or unsalted for the final layer)
+        const bool final_layer = (cur_n / 2 == final_size);
+        const int hash_mode = d_nodes ? (final_layer || !salt_ptr ? 1 : 2) : 0;
+        CK(fri_fold_coset(cur, next, cur_n, limbs, (int)log_m, x0, beta, 1, 0, s, hash_mode, salt_ptr, node_ptr));
         g_launches++;
         x0 = bb::mul(x0, x0);  // :228-231: x <- x^2
         log_m--;
         cur_n /= 2;
         folds++;
         if (d_nodes) {
-            const bool final_layer = (cur_n == final_size);  // :234-238
-            CK(merkle_commit(next, limbs, cur_n, final_layer ? nullptr : salt_ptr, node_ptr, s));
-            g_launches += 1 + (unsigned)levels_of(cur_n);
+            CK(merkle_upper_levels(node_ptr, cur_n, s));
+            g_launches += (unsigned)levels_of(cur_n);
             if (roots_out || challenge) {
                 CK(root_to_host(node_ptr, cur_n, root, s));
                 if (roots_out) memcpy(roots_out + 32 * folds, root, 32);

@@ -6,7 +6,9 @@
 // A general-xs form (arbitrary evaluation points, per-element Fermat inverse) keeps the reference signature.
 #include "fri_fold.cuh"
 
+#include "merkle.cuh"
 #include "ntt_pass.cuh"
+#include "sha256.cuh"
 
 namespace bb {
 
@@ -15,13 +17,27 @@ struct FoldIdx {
     uint32_t idx_mul, idx_add, shift;
 };
 
+// HASH: 0 fold only; 1 also write the unsalted leaf digest of the new value; 2 the salted one ("fold and next layer's
+// leaves" in one kernel: the folded value is hashed while it is still in registers)
+template <int HASH>
 __global__ void __launch_bounds__(256) fold_base_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                        size_t half, PowTable winv, FoldIdx fi, uint32_t c_m) {
+                                                        size_t half, PowTable winv, FoldIdx fi, uint32_t c_m,
+                                                        const uint4* __restrict__ salts, uint8_t* __restrict__ leaf_nodes) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= half) return;
     uint32_t a = in[i], b = in[i + half];
     uint32_t tw = monty_mul(pow_lookup(winv, ((uint32_t)i * fi.idx_mul + fi.idx_add) << fi.shift), c_m);  // Montgomery form
-    out[i] = add(halve(add(a, b)), monty_mul(sub(a, b), tw));
+    const uint32_t r = add(halve(add(a, b)), monty_mul(sub(a, b), tw));
+    out[i] = r;
+    if (HASH) {
+        uint32_t v[1] = {r};
+        Sha s;
+        if (HASH == 2)
+            leaf_digest<1, true>(v, salts[i], s);
+        else
+            leaf_digest<1, false>(v, make_uint4(0, 0, 0, 0), s);
+        store_digest(leaf_nodes + 32 * i, s);
+    }
 }
 
 // Ext * (Ext constant): out_k = sum_j d_j * C[k][j] with C the 4x4 multiplication matrix of the constant
@@ -55,9 +71,10 @@ __device__ __forceinline__ Ext ext_mul_const(const Ext& d, const ExtMat& c) {
 }
 
 // PER_THREAD outputs per thread: more independent 16-byte loads in flight per warp
-template <int PER_THREAD>
+template <int PER_THREAD, int HASH>
 __global__ void __launch_bounds__(256) fold_ext_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t half,
-                                                       PowTable winv, FoldIdx fi, ExtMat cm) {
+                                                       PowTable winv, FoldIdx fi, ExtMat cm, const uint4* __restrict__ salts,
+                                                       uint8_t* __restrict__ leaf_nodes) {
     const size_t i0 = ((size_t)blockIdx.x * blockDim.x) * PER_THREAD + threadIdx.x;
     uint4 av[PER_THREAD], bv[PER_THREAD];
 #pragma unroll
@@ -84,6 +101,15 @@ __global__ void __launch_bounds__(256) fold_ext_kernel(const uint4* __restrict__
         r.z = add(halve(s.c[2]), t.c[2]);
         r.w = add(halve(s.c[3]), t.c[3]);
         out[i] = r;
+        if (HASH) {
+            uint32_t v[4] = {r.x, r.y, r.z, r.w};
+            Sha h;
+            if (HASH == 2)
+                leaf_digest<4, true>(v, salts[i], h);
+            else
+                leaf_digest<4, false>(v, make_uint4(0, 0, 0, 0), h);
+            store_digest(leaf_nodes + 32 * i, h);
+        }
     }
 }
 
@@ -132,7 +158,8 @@ __global__ void __launch_bounds__(256) fold_ext_xs_kernel(const uint4* __restric
 static inline unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
 
 int fri_fold_coset(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int limbs, int log_m_global, uint32_t x0,
-                   const uint32_t beta[4], uint32_t idx_mul, uint32_t idx_add, cudaStream_t s) {
+                   const uint32_t beta[4], uint32_t idx_mul, uint32_t idx_add, cudaStream_t s, int hash_mode,
+                   const uint8_t* d_salts, uint8_t* d_leaf_nodes) {
     if (m_local < 2 || (m_local & 1) || log_m_global < 1 || log_m_global > MAX_LOG_N || x0 == 0) return (int)cudaErrorInvalidValue;
     PowTable winv;
     // omega_m^-t table; shared with the inverse NTT of the same size
@@ -142,7 +169,14 @@ int fri_fold_coset(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int li
     const uint32_t hx = bb::mul(HALF, bb::inv(x0));  // (1/2) * x0^-1
     FoldIdx fi{idx_mul, idx_add, 0};
     if (limbs == 1) {
-        fold_base_kernel<<<blocks_for(half), 256, 0, s>>>(d_in, d_out, half, winv, fi, to_monty(bb::mul(hx, beta[0])));
+        const uint32_t cmul = to_monty(bb::mul(hx, beta[0]));
+        const uint4* sl = reinterpret_cast<const uint4*>(d_salts);
+        if (hash_mode == 2)
+            fold_base_kernel<2><<<blocks_for(half), 256, 0, s>>>(d_in, d_out, half, winv, fi, cmul, sl, d_leaf_nodes);
+        else if (hash_mode == 1)
+            fold_base_kernel<1><<<blocks_for(half), 256, 0, s>>>(d_in, d_out, half, winv, fi, cmul, sl, d_leaf_nodes);
+        else
+            fold_base_kernel<0><<<blocks_for(half), 256, 0, s>>>(d_in, d_out, half, winv, fi, cmul, sl, d_leaf_nodes);
     } else {
         // multiplication matrix of c = beta * (1/2 x0^-1): (d*c)_k = sum_j d_j c_(k-j), wrapped terms times W = 11
         uint32_t c[4];
@@ -154,7 +188,14 @@ int fri_fold_coset(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int li
                 cm.m[k][j] = to_monty(v);
             }
         constexpr int PT = 2;
-        fold_ext_kernel<PT><<<(unsigned)((half + 256 * PT - 1) / (256 * PT)), 256, 0, s>>>((const uint4*)d_in, (uint4*)d_out, half, winv, fi, cm);
+        const unsigned blocks = (unsigned)((half + 256 * PT - 1) / (256 * PT));
+        const uint4* sl = reinterpret_cast<const uint4*>(d_salts);
+        if (hash_mode == 2)
+            fold_ext_kernel<PT, 2><<<blocks, 256, 0, s>>>((const uint4*)d_in, (uint4*)d_out, half, winv, fi, cm, sl, d_leaf_nodes);
+        else if (hash_mode == 1)
+            fold_ext_kernel<PT, 1><<<blocks, 256, 0, s>>>((const uint4*)d_in, (uint4*)d_out, half, winv, fi, cm, sl, d_leaf_nodes);
+        else
+            fold_ext_kernel<PT, 0><<<blocks, 256, 0, s>>>((const uint4*)d_in, (uint4*)d_out, half, winv, fi, cm, sl, d_leaf_nodes);
     }
     return (int)cudaGetLastError();
 }

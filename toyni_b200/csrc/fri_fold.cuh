@@ -9,8 +9,11 @@ namespace bb {
 // Fold a layer whose evaluation points are x_i = x0 * omega_m^i (m = 2^log_m_global).  `d_in` holds m_local
 // values of `limbs` u32 each; local index t stands for global index t*idx_mul + idx_add (1, 0 on one GPU;
 // G, rank for the cyclic multi-GPU layout).  Pairs are (t, t + m_local/2).
+// hash_mode: 0 fold only; 1 / 2 also write the unsalted / salted leaf digest of every new value to d_leaf_nodes
+// (the leaf level of the next layer's Merkle tree) from the same kernel.
 int fri_fold_coset(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int limbs, int log_m_global, uint32_t x0,
-                   const uint32_t beta[4], uint32_t idx_mul, uint32_t idx_add, cudaStream_t s);
+                   const uint32_t beta[4], uint32_t idx_mul, uint32_t idx_add, cudaStream_t s, int hash_mode = 0,
+                   const uint8_t* d_salts = nullptr, uint8_t* d_leaf_nodes = nullptr);
 // Reference signature: arbitrary evaluation points xs[0..m/2) on the device.
 int fri_fold_xs(const uint32_t* d_in, const uint32_t* d_xs, uint32_t* d_out, size_t m, int limbs, const uint32_t beta[4],
                 cudaStream_t s);

@@ -8,102 +8,27 @@
 // live back to back in one device array.
 #include "merkle.cuh"
 
+#include "sha256.cuh"
+
 namespace bb {
 
-__constant__ uint32_t K256[64] = {
-    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
-    0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
-    0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
-    0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
-    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
-    0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
-    0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
-
-__device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
-__device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
-
-struct Sha {
-    uint32_t h[8];
-};
-
-__device__ __forceinline__ void sha_init(Sha& s) {
-    s.h[0] = 0x6a09e667; s.h[1] = 0xbb67ae85; s.h[2] = 0x3c6ef372; s.h[3] = 0xa54ff53a;
-    s.h[4] = 0x510e527f; s.h[5] = 0x9b05688c; s.h[6] = 0x1f83d9ab; s.h[7] = 0x5be0cd19;
-}
-
-// FIPS 180-4 compression with a rolling 16-word schedule, fully unrolled so constant words fold away
-__device__ __forceinline__ void sha_compress(Sha& s, uint32_t w[16]) {
-    uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
-#pragma unroll
-    for (int i = 0; i < 64; i++) {
-        uint32_t wi;
-        if (i < 16) {
-            wi = w[i];
-        } else {
-            uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
-            uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
-            uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
-            wi = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
-            w[i & 15] = wi;
-        }
-        uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
-        uint32_t ch = (e & f) ^ (~e & g);
-        uint32_t t1 = h + S1 + ch + K256[i] + wi;
-        uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
-        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-        uint32_t t2 = S0 + mj;
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
-    }
-    s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
-}
-
-__device__ __forceinline__ void store_digest(uint8_t* dst, const Sha& s) {
-    uint4* o = reinterpret_cast<uint4*>(dst);  // 32-byte aligned
-    o[0] = make_uint4(bswap(s.h[0]), bswap(s.h[1]), bswap(s.h[2]), bswap(s.h[3]));
-    o[1] = make_uint4(bswap(s.h[4]), bswap(s.h[5]), bswap(s.h[6]), bswap(s.h[7]));
-}
-
-// Leaf hash of one field value.  The byte stream after the tag is a sequence of little-endian words q[]:
-// salt (4 words, optional) then (value, 0) per limb; big-endian message word i is (bs[i-1] << 24) | (bs[i] >> 8)
-// with bs = bswap(q) and bs[-1] = tag.
+// Leaf hash of one field value (leaf_digest in sha256.cuh).
 template <int LIMBS, bool SALTED>
 __global__ void __launch_bounds__(256) leaf_hash_kernel(const uint32_t* __restrict__ vals, const uint4* __restrict__ salts,
                                                         uint8_t* __restrict__ nodes, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    constexpr int NQ = (SALTED ? 4 : 0) + 2 * LIMBS;  // stream words
-    uint32_t q[NQ + 1];
-    int k = 0;
-    if (SALTED) {
-        uint4 sv = salts[i];
-        q[k++] = sv.x; q[k++] = sv.y; q[k++] = sv.z; q[k++] = sv.w;
-    }
+    uint32_t v[LIMBS];
     if (LIMBS == 1) {
-        q[k++] = vals[i];
-        q[k++] = 0;
+        v[0] = vals[i];
     } else {
-        uint4 v = reinterpret_cast<const uint4*>(vals)[i];
-        q[k++] = v.x; q[k++] = 0; q[k++] = v.y; q[k++] = 0; q[k++] = v.z; q[k++] = 0; q[k++] = v.w; q[k++] = 0;
+        uint4 t = reinterpret_cast<const uint4*>(vals)[i];
+        v[0] = t.x; v[LIMBS > 1 ? 1 : 0] = t.y; v[LIMBS > 2 ? 2 : 0] = t.z; v[LIMBS > 3 ? 3 : 0] = t.w;
     }
-    q[NQ] = 0x80u;  // padding byte right after the message
-    uint32_t w[16];
-    uint32_t prev = 0x00u;  // LEAF_TAG
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        if (j <= NQ) {
-            uint32_t cur = bswap(q[j]);
-            w[j] = (prev << 24) | (cur >> 8);
-            prev = cur;
-        } else if (j == NQ + 1) {
-            w[j] = prev << 24;  // last byte of the 0x80 word (zero) spills over: always 0
-        } else {
-            w[j] = 0;
-        }
-    }
-    w[15] = (uint32_t)((1 + 4 * NQ) * 8);  // message length in bits (NQ <= 12, so word 15 is free)
+    uint4 sv = make_uint4(0, 0, 0, 0);
+    if (SALTED) sv = salts[i];
     Sha s;
-    sha_init(s);
-    sha_compress(s, w);
+    leaf_digest<LIMBS, SALTED>(v, sv, s);
     store_digest(nodes + 32 * i, s);
 }
 
@@ -203,7 +128,7 @@ size_t merkle_node_count(size_t nleaves) {
     return total;
 }
 
-static int upper_levels(uint8_t* d_nodes, size_t n, cudaStream_t s) {
+int merkle_upper_levels(uint8_t* d_nodes, size_t n, cudaStream_t s) {
     uint8_t* cur = d_nodes;
     size_t cur_n = n;
     while (cur_n > 1) {
@@ -230,7 +155,7 @@ int merkle_commit(const uint32_t* d_vals, int limbs, size_t n, const uint8_t* d_
         leaf_hash_kernel<4, false><<<blocks, 256, 0, s>>>(d_vals, salts, d_nodes, n);
     int rc = (int)cudaGetLastError();
     if (rc) return rc;
-    return upper_levels(d_nodes, n, s);
+    return merkle_upper_levels(d_nodes, n, s);
 }
 
 int merkle_build_bytes(const uint8_t* d_leaves, size_t n, size_t leaf_len, uint8_t* d_nodes, cudaStream_t s) {
@@ -238,7 +163,7 @@ int merkle_build_bytes(const uint8_t* d_leaves, size_t n, size_t leaf_len, uint8
     leaf_hash_bytes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_leaves, n, leaf_len, d_nodes);
     int rc = (int)cudaGetLastError();
     if (rc) return rc;
-    return upper_levels(d_nodes, n, s);
+    return merkle_upper_levels(d_nodes, n, s);
 }
 
 int merkle_open(const uint8_t* d_nodes, size_t nleaves, size_t index, uint8_t* d_path, uint8_t* h_pos, size_t* depth,
