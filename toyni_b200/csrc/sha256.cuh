@@ -15,6 +15,19 @@ static __constant__ uint32_t K256[64] = {
     0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
 
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+// SHA-256 is ALU-pipe bound on sm_100 (rotates and LOP3 only run there: ~980 of the ~1330 instructions of a
+// compression); its ~350 additions are steered to the otherwise idle FMA pipe by writing them as a*1+b with a
+// multiplier the compiler cannot see through (a __constant__ word that happens to hold 1).
+static __constant__ uint32_t c_sha_one = 1u;
+__device__ __forceinline__ uint32_t fadd(uint32_t a, uint32_t b) {
+#ifdef BB_SHA_PLAIN_ADD
+    return a + b;
+#else
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(c_sha_one), "r"(b));
+    return r;
+#endif
+}
 __device__ __forceinline__ uint32_t bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
 struct Sha {
@@ -38,16 +51,16 @@ __device__ __forceinline__ void sha_compress(Sha& s, uint32_t w[16]) {
             uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
             uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
             uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
-            wi = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+            wi = fadd(fadd(w[i & 15], s0), fadd(w[(i - 7) & 15], s1));
             w[i & 15] = wi;
         }
         uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
         uint32_t ch = (e & f) ^ (~e & g);
-        uint32_t t1 = h + S1 + ch + K256[i] + wi;
+        uint32_t t1 = fadd(fadd(fadd(h, S1), fadd(ch, K256[i])), wi);
         uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
         uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-        uint32_t t2 = S0 + mj;
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        uint32_t t2 = fadd(S0, mj);
+        h = g; g = f; f = e; e = fadd(d, t1); d = c; c = b; b = a; a = fadd(t1, t2);
     }
     s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
