@@ -407,6 +407,10 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
         const bool aligned = ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) && (src_bs % 4 == 0) && (dst_bs % 4 == 0);
         if (!transposed && lc >= 2 && aligned && p.log_pfull != 1 && (p.ncols & ((1u << lc) - 1u)) == 0 && !g_force_scalar)
             fn = pass_launcher_v4(lr, lc);
+        if (fn && first && !inv && lr >= 6 && lr <= 9 && d.n_in * 32 == n && p.in_batch_stride % 4 == 0) {
+            // exactly the first R/32 rows of every tile hold input (blowup 32): prune the copy-only stages
+            p.prune_log = 5;
+        }
         if (!fn && p.epi_mode == EPI_FOURSTEP) return (int)cudaErrorInvalidConfiguration;
         if (!fn) fn = pass_launcher(lr, lc);
         if (!fn) return (int)cudaErrorInvalidConfiguration;

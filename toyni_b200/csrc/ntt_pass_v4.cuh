@@ -423,15 +423,33 @@ __global__ void __launch_bounds__(V4<LR, LC>::NT) ntt_pass_v4_kernel(const PassP
             __syncthreads();
         }
 
-        // ---- radix-16 DIT rounds, strides 1, 16, 256
-        if constexpr (T::G1 > 0) dit_round_v4<LR, LC, 0, T::G1>(smv, stw, p);
-        if constexpr (T::G2 > 0) {
-            __syncthreads();
-            dit_round_v4<LR, LC, 4, T::G2>(smv, stw, p);
+        bool pruned = false;
+        if constexpr (LR >= 6 && LR <= 9) {
+            // Blowup-32 LDE, first pass: only rows d < R/32 hold input, i.e. (bit-reversed) rows 32m.  The first five
+            // DIT stages then only copy x_m over rows 32m..32m+31 (every butterfly has a zero odd input), so they are
+            // replaced by that copy and ONE round of the remaining LR-5 stages (stride 32).
+            if (p.prune_log == 5) {
+                pruned = true;
+#pragma unroll 1
+                for (int i = tid; i < R * CV; i += NT) {
+                    const uint32_t cv = i & (CV - 1), r = i >> LCV;
+                    if (r & 31u) smv[T::chunk(r, cv)] = smv[T::chunk(r & ~31u, cv)];
+                }
+                __syncthreads();
+                dit_round_v4<LR, LC, 5, LR - 5>(smv, stw, p);
+            }
         }
-        if constexpr (T::G3 > 0) {
-            __syncthreads();
-            dit_round_v4<LR, LC, 8, T::G3>(smv, stw, p);
+        if (!pruned) {
+            // ---- radix-16 DIT rounds, strides 1, 16, 256
+            if constexpr (T::G1 > 0) dit_round_v4<LR, LC, 0, T::G1>(smv, stw, p);
+            if constexpr (T::G2 > 0) {
+                __syncthreads();
+                dit_round_v4<LR, LC, 4, T::G2>(smv, stw, p);
+            }
+            if constexpr (T::G3 > 0) {
+                __syncthreads();
+                dit_round_v4<LR, LC, 8, T::G3>(smv, stw, p);
+            }
         }
         __syncthreads();
 
