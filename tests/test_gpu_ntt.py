@@ -269,3 +269,28 @@ def test_fourstep_paths_on_one_gpu(D, log_n):
         out = fs.run(D.to_device(MG.fourstep_scatter(x, 0, 1)), inverse=inv)
         assert np.array_equal(MG.fourstep_gather([D.to_host(out)], log_n), ref)
         fs.close()
+
+
+def test_two_contexts_on_two_threads_do_not_share_scratch():
+    """The reference's context is not re-entrant and its callers are single threaded (src/ntt.rs:118-120); here two
+    sizes driven from two host threads at once must both come out right (per-context stream and scratch)."""
+    import threading
+    from toyni_b200 import ntt
+    results = {}
+
+    def work(log_n, reps):
+        x = O.random_field(1 << log_n, seed=log_n)
+        ref = O.ntt(x, threads=2)
+        ok = True
+        for _ in range(reps):
+            v = x.copy()
+            ntt.ntt_cuda(v)
+            ok &= bool(np.array_equal(v, ref))
+        results[log_n] = ok
+
+    ts = [threading.Thread(target=work, args=(18, 6)), threading.Thread(target=work, args=(19, 4))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert results == {18: True, 19: True}

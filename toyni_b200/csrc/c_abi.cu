@@ -16,7 +16,7 @@ using namespace bb;
 // ------------------------------------------------------------------ library state
 static std::atomic<int> g_last_error{0};
 static std::atomic<unsigned long long> g_launches{0};
-static std::atomic<cudaStream_t> g_stream{nullptr};
+static thread_local cudaStream_t g_stream = nullptr;  // per host thread, as the header says
 
 static inline int note(int rc) {
     if (rc != 0) {
@@ -31,7 +31,7 @@ static inline int note(int rc) {
         if (rc_ != 0) return note(rc_);        \
     } while (0)
 
-static inline cudaStream_t cur_stream() { return g_stream.load(); }
+static inline cudaStream_t cur_stream() { return g_stream; }
 static inline bool is_pow2(size_t v) { return v && !(v & (v - 1)); }
 static inline uint32_t log2_of(size_t v) {
     uint32_t l = 0;
@@ -98,7 +98,7 @@ void* ntt_ctx_create(uint32_t n) {
     c->d32 = nullptr;
     c->stream = nullptr;
     if (note((int)cudaMalloc(&c->d64, (size_t)n * 8)) || note((int)cudaMalloc(&c->d32, (size_t)n * 4)) ||
-        note((int)cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) || note(engine_warmup((int)log_n))) {
+        note((int)cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) || note(engine_warmup((int)log_n, c->stream))) {
         ntt_ctx_destroy(c);
         return nullptr;
     }
@@ -110,6 +110,7 @@ void ntt_ctx_destroy(void* ctx) {
     if (!c) return;
     if (c->stream) {
         cudaStreamSynchronize(c->stream);
+        engine_drop_stream(c->stream);
         cudaStreamDestroy(c->stream);
     }
     cudaFree(c->d64);
@@ -158,7 +159,7 @@ int bb_device_ok(void) {
     if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
     return major == 10;
 }
-void bb_set_stream(void* cuda_stream) { g_stream.store((cudaStream_t)cuda_stream); }
+void bb_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
 int bb_sync(void) { return note((int)cudaStreamSynchronize(cur_stream())); }
 
 int bb_dev_alloc(void** d_ptr, size_t bytes) { return note((int)cudaMalloc(d_ptr, bytes)); }
@@ -424,7 +425,7 @@ int bb_ntt_launches(uint32_t log_n) { return ntt_plan_for((int)log_n, 0, 1).npas
 unsigned long long bb_kernel_launch_count(void) { return g_launches.load(); }
 int bb_warmup(uint32_t log_n) {
     if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
-    return note(engine_warmup((int)log_n));
+    return note(engine_warmup((int)log_n, cur_stream()));
 }
 void bb_release(void) { engine_release(); }
 

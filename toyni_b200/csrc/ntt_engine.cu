@@ -53,8 +53,9 @@ struct DeviceState {
     uint2* tw[2] = {nullptr, nullptr};  // omega_4096^(+-i), i < 2048
     uint2 tw16[2][8];
     std::map<std::tuple<uint32_t, int, uint32_t>, PowTab> pow_tabs;  // (g, log_total, scale) -> tables
-    uint32_t* scratch = nullptr;
-    size_t scratch_words = 0;
+    // one scratch buffer per stream: transforms on different streams (e.g. two legacy contexts used from two host
+    // threads) may execute concurrently and must not share the intermediate array
+    std::map<cudaStream_t, std::pair<uint32_t*, size_t>> scratch;
     bool ready = false;
 };
 
@@ -118,18 +119,19 @@ static int pow_table_get(DeviceState& st, uint32_t g, int log_total, uint32_t sc
     return 0;
 }
 
-static int scratch_get(DeviceState& st, size_t words, uint32_t** out) {
-    if (st.scratch_words < words) {
-        if (st.scratch) {
-            BB_CK(cudaDeviceSynchronize());
-            BB_CK(cudaFree(st.scratch));
-            st.scratch = nullptr;
-            st.scratch_words = 0;
+static int scratch_get(DeviceState& st, cudaStream_t stream, size_t words, uint32_t** out) {
+    auto& slot = st.scratch[stream];
+    if (slot.second < words) {
+        if (slot.first) {
+            BB_CK(cudaStreamSynchronize(stream));
+            BB_CK(cudaFree(slot.first));
+            slot.first = nullptr;
+            slot.second = 0;
         }
-        BB_CK(cudaMalloc(&st.scratch, words * sizeof(uint32_t)));
-        st.scratch_words = words;
+        BB_CK(cudaMalloc(&slot.first, words * sizeof(uint32_t)));
+        slot.second = words;
     }
-    *out = st.scratch;
+    *out = slot.first;
     return 0;
 }
 
@@ -146,7 +148,10 @@ size_t engine_scratch_bytes() {
     int dev = 0;
     cudaGetDevice(&dev);
     auto it = g_states.find(dev);
-    return it == g_states.end() ? 0 : it->second.scratch_words * sizeof(uint32_t);
+    size_t total = 0;
+    if (it != g_states.end())
+        for (auto& kv : it->second.scratch) total += kv.second.second * sizeof(uint32_t);
+    return total;
 }
 
 void engine_release() {
@@ -162,7 +167,7 @@ void engine_release() {
         cudaFree(kv.second.lo);
         cudaFree(kv.second.hi);
     }
-    cudaFree(st.scratch);
+    for (auto& kv : st.scratch) cudaFree(kv.second.first);
     g_states.erase(it);
 }
 
@@ -238,14 +243,27 @@ NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch) {
 }
 
 // ------------------------------------------------------------------ executor
-int engine_warmup(int log_n) {
+void engine_drop_stream(cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto it = g_states.find(dev);
+    if (it == g_states.end()) return;
+    auto sc = it->second.scratch.find(stream);
+    if (sc == it->second.scratch.end()) return;
+    cudaStreamSynchronize(stream);
+    cudaFree(sc->second.first);
+    it->second.scratch.erase(sc);
+}
+
+int engine_warmup(int log_n, cudaStream_t stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     DeviceState* st;
     int rc = state_get(&st);
     if (rc) return rc;
     if (log_n > MAX_LR) {
         uint32_t* s;
-        rc = scratch_get(*st, (size_t)1 << log_n, &s);
+        rc = scratch_get(*st, stream, (size_t)1 << log_n, &s);
         if (rc) return rc;
         for (int inv = 0; inv < 2; inv++) {
             uint32_t w = root_of_unity(log_n);
@@ -311,7 +329,7 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
 
     uint32_t* scratch = nullptr;
     if (pl.npass > 1) {
-        rc = scratch_get(*st, n * inner * d.batch, &scratch);
+        rc = scratch_get(*st, stream, n * inner * d.batch, &scratch);
         if (rc) return rc;
     }
 

@@ -50,7 +50,8 @@ void ntt_plan_override(int log_n, const NttPlan& plan);
 PassLaunchFn pass_launcher(int lr, int lc);     // scalar kernel; nullptr if that tile shape is not built
 PassLaunchFn pass_launcher_v4(int lr, int lc);  // vectorised kernel (LC >= 2)
 void engine_force_scalar(bool on);            // test hook
-int engine_warmup(int log_n);                // build tables / scratch ahead of time
+int engine_warmup(int log_n, cudaStream_t stream);  // build tables / this stream's scratch ahead of time
+void engine_drop_stream(cudaStream_t stream);       // free the scratch kept for a stream that is going away
 size_t engine_scratch_bytes();
 void engine_release();                       // free every cached device allocation on the current device
 
