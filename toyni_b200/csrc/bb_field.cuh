@@ -78,6 +78,19 @@ BB_HD uint32_t root_of_unity(uint32_t log_n) { return pow(GEN27, 1ull << (27 - l
 // Shoup companion of a constant w < p: floor(w * 2^32 / p)
 BB_HD uint32_t shoup_companion(uint32_t w) { return (uint32_t)(((uint64_t)w << 32) / P); }
 
+// The same companion for a canonical w without a 64-bit division (device-side twiddle generation):
+// q^ = floor(w K / 2^31) with K = floor(2^63 / p) = 2^32 + KLO is q or q - 1, and the remainder
+// w 2^32 - q^ p < 2p fits 32 bits, so one comparison settles it.
+BB_HD uint32_t shoup_companion_fast(uint32_t w) {
+    constexpr uint64_t K = (1ull << 63) / P;
+    static_assert((K >> 32) == 1, "K = 2^32 + KLO");
+    constexpr uint32_t KLO = (uint32_t)K;
+    const uint64_t y = (uint64_t)w * KLO;
+    uint32_t q = (w << 1) + (uint32_t)(y >> 31);
+    const uint32_t rem = 0u - q * P;
+    return rem >= P ? q + 1u : q;
+}
+
 // x*w mod p in [0,2p) for ANY 32-bit x, given wp = shoup_companion(w)
 BB_HD uint32_t shoup_mul_lazy(uint32_t x, uint32_t w, uint32_t wp) {
 #ifdef __CUDA_ARCH__

@@ -2,6 +2,7 @@
 #include "ntt_engine.cuh"
 
 #include "fri_fold.cuh"
+#include "ntt_pass_v5.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -42,6 +43,20 @@ __global__ void gen_shoup_kernel(uint2* out, uint32_t count, uint32_t g_m) {
     }
 }
 
+// btab[e*8 + c] = Shoup pair of g^(c*e): the column-dependent factor of the first pass's inter-pass twiddle
+// (ntt_pass_v5.cuh)
+__global__ void gen_btab_kernel(uint2* out, uint32_t g_m) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (uint32_t)(V5_R * 8)) {
+        uint32_t w = from_monty(monty_pow_dev(g_m, (i >> 3) * (i & 7u)));
+        out[i] = make_uint2(w, shoup_companion(w));
+    }
+}
+
+extern template int launch_pass_v5<V5_ROWS_CANON>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
+extern template int launch_pass_v5<V5_ROWS_TWIDDLE>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
+extern template int launch_pass_v5<V5_COLS_TWIDDLE>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
+
 // ------------------------------------------------------------------ per-device state
 struct PowTab {
     uint2* lo = nullptr;
@@ -56,6 +71,7 @@ struct DeviceState {
     // one scratch buffer per stream: transforms on different streams (e.g. two legacy contexts used from two host
     // threads) may execute concurrently and must not share the intermediate array
     std::map<cudaStream_t, std::pair<uint32_t*, size_t>> scratch;
+    std::map<uint32_t, uint2*> btabs;  // g -> table of g^(c*e), c < 8, e < 256
     bool ready = false;
 };
 
@@ -63,6 +79,8 @@ static std::mutex g_mu;
 static std::map<int, DeviceState> g_states;
 static std::map<int, NttPlan> g_plan_override;
 static bool g_force_scalar = false;  // test hook: run every pass on the scalar kernel
+static int g_v5 = -1;                // warp-private kernel for R = 256 passes (TOYNI_NTT_V5=0 switches it off)
+static uint32_t g_v5_min_strips = 2048;
 
 #define BB_CK(x)                          \
     do {                                  \
@@ -119,6 +137,20 @@ static int pow_table_get(DeviceState& st, uint32_t g, int log_total, uint32_t sc
     return 0;
 }
 
+static int btab_get(DeviceState& st, uint32_t g, const uint2** out) {
+    auto it = st.btabs.find(g);
+    if (it == st.btabs.end()) {
+        uint2* t = nullptr;
+        BB_CK(cudaMalloc(&t, sizeof(uint2) * V5_R * 8));
+        gen_btab_kernel<<<(V5_R * 8 + 255) / 256, 256>>>(t, to_monty(g));
+        BB_CK(cudaGetLastError());
+        BB_CK(cudaDeviceSynchronize());
+        it = st.btabs.emplace(g, t).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
 static int scratch_get(DeviceState& st, cudaStream_t stream, size_t words, uint32_t** out) {
     auto& slot = st.scratch[stream];
     if (slot.second < words) {
@@ -168,6 +200,7 @@ void engine_release() {
         cudaFree(kv.second.hi);
     }
     for (auto& kv : st.scratch) cudaFree(kv.second.first);
+    for (auto& kv : st.btabs) cudaFree(kv.second);
     g_states.erase(it);
 }
 
@@ -235,6 +268,12 @@ static NttPlan plan_locked(int log_n, int log_inner, size_t batch) {
         pl.lc[i] = pick_lc(pl.lr[i], want);
     }
     return pl;
+}
+
+void engine_enable_v5(int on, uint32_t min_strips) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_v5 = on ? 1 : 0;
+    if (min_strips) g_v5_min_strips = min_strips;
 }
 
 NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch) {
@@ -420,9 +459,34 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
         } else {
             p.epi_mode = EPI_NONE;
         }
+        const bool aligned = ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) && (src_bs % 4 == 0) && (dst_bs % 4 == 0);
+        // warp-private kernel: full-length 256-point passes of large transforms (plain twiddle or no epilogue)
+        if (g_v5 < 0) {
+            const char* e = getenv("TOYNI_NTT_V5");
+            g_v5 = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (g_v5 && !g_force_scalar && !transposed && lr == V5_LR && aligned && p.pro_mode == PRO_NONE &&
+            (!first || d.n_in == n) && (p.ncols % 32u) == 0 &&
+            (size_t)(p.ncols / 8u) * d.batch >= g_v5_min_strips && (size_t)(p.ncols / 8u) * d.batch < (1ull << 31) &&
+            ((p.epi_mode == EPI_NONE && p.log_pfull >= 3) ||
+             (p.epi_mode == EPI_TWIDDLE && (p.log_pfull >= 3 || (p.log_pfull == 0 && d.log_inner == 0))))) {
+            const uint32_t strips_x = p.ncols / 8u;
+            if (p.epi_mode == EPI_NONE) {
+                rc = launch_pass_v5<V5_ROWS_CANON>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
+            } else if (p.log_pfull >= 3) {
+                rc = launch_pass_v5<V5_ROWS_TWIDDLE>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
+            } else {
+                const uint2* btab = nullptr;
+                rc = btab_get(*st, bb::pow(omega, 1ull << p.epi_shift), &btab);
+                if (rc) return rc;
+                rc = launch_pass_v5<V5_COLS_TWIDDLE>(p, btab, strips_x, (uint32_t)d.batch, stream);
+            }
+            if (rc) return rc;
+            log_p += lr;
+            continue;
+        }
         // vectorised kernel whenever chunks of four columns stay whole; scalar kernel otherwise
         PassLaunchFn fn = nullptr;
-        const bool aligned = ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) && (src_bs % 4 == 0) && (dst_bs % 4 == 0);
         if (!transposed && lc >= 2 && aligned && p.log_pfull != 1 && (p.ncols & ((1u << lc) - 1u)) == 0 && !g_force_scalar)
             fn = pass_launcher_v4(lr, lc);
         if (fn && first && !inv && lr >= 6 && lr <= 9 && d.n_in * 32 == n && p.in_batch_stride % 4 == 0) {

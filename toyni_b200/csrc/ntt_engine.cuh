@@ -49,7 +49,9 @@ NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch);
 void ntt_plan_override(int log_n, const NttPlan& plan);
 PassLaunchFn pass_launcher(int lr, int lc);     // scalar kernel; nullptr if that tile shape is not built
 PassLaunchFn pass_launcher_v4(int lr, int lc);  // vectorised kernel (LC >= 2)
-void engine_force_scalar(bool on);            // test hook
+// R = 256 passes of large transforms run on the warp-private kernel (ntt_pass_v5.cuh) when at least `min_strips`
+// strips of 8 columns exist (0 keeps the current threshold); on = 0 sends them to the tile kernel instead
+void engine_enable_v5(int on, uint32_t min_strips);
 int engine_warmup(int log_n, cudaStream_t stream);  // build tables / this stream's scratch ahead of time
 void engine_drop_stream(cudaStream_t stream);       // free the scratch kept for a stream that is going away
 size_t engine_scratch_bytes();

@@ -62,6 +62,7 @@ _SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)], C.c_int),
     "bb_ntt_set_plan": ([C.c_uint32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     "bb_ntt_get_plan": ([C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+    "bb_ntt_set_kernel": ([C.c_int, C.c_uint32], None),
     "bb_ntt_launches": ([C.c_uint32], C.c_int),
     "bb_kernel_launch_count": ([], C.c_ulonglong),
     "bb_warmup": ([C.c_uint32], C.c_int),
@@ -79,7 +80,7 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 
 def library_path():
-    return os.path.join(_HERE, "libntt_cuda.so")
+    return os.environ.get("TOYNI_NTT_LIB") or os.path.join(_HERE, "libntt_cuda.so")  # env: tuning builds only
 
 
 class ToyniCudaError(RuntimeError):
