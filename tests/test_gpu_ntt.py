@@ -252,6 +252,39 @@ def test_ntt_2_24_against_oracle_checksum(D):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_warp_private_pass_kernels_match_oracle_and_tile_kernel(D, kernel):
+    """The two warp-private 256-point pass kernels (ntt_pass_v5.cuh: 8-column strips, ntt_pass_v6.cuh: 16-column
+    strips) are selectable alternatives to the tile kernel; same PassParams contract, so same bits.  Sizes whose plans
+    contain 256-point passes: 2^16 batched (256 x 256), 2^22 (256 x 128 x 128), 2^24 (256^3), AoS Ext 2^24."""
+    import torch
+    from toyni_b200.lib import lib
+    L = lib()
+    try:
+        # (a) against the oracle: every vector of a 2^16 batch, forward and inverse
+        x = O.random_field(64 << 16, seed=99 + kernel).reshape(64, 1 << 16)
+        for inv in (False, True):
+            L.bb_ntt_set_kernel(kernel, 1)
+            got = D.to_host(D.ntt_batch_(D.to_device(x), inv))
+            for r in (0, 17, 63):
+                ref = O.intt(x[r], threads=4) if inv else O.ntt(x[r], threads=4)
+                assert np.array_equal(got[r], ref)
+        # (b) against the tile kernel (itself checked against the oracle at every size): whole vectors, bit for bit
+        g = torch.Generator(device="cuda")
+        g.manual_seed(5 + kernel)
+        for shape, fn in (((1 << 22,), D.ntt_), ((1 << 24,), D.ntt_), ((1 << 24, 4), D.ntt_ext_), ((3, 1 << 24), D.ntt_batch_)):
+            t = torch.randint(0, P, shape, dtype=torch.int32, device="cuda", generator=g)
+            for inv in (False, True):
+                L.bb_ntt_set_kernel(0, 0)
+                a = fn(t.clone(), inv)
+                L.bb_ntt_set_kernel(kernel, 0)
+                b = fn(t.clone(), inv)
+                assert torch.equal(a, b)
+                assert int(b.max()) < P and int(b.min()) >= 0
+    finally:
+        L.bb_ntt_set_kernel(0, 2048)
+
+
 # ------------------------------------------------------------------ four-step building blocks (multi-GPU layer)
 @pytest.mark.parametrize("log_n", [10, 16, 21])
 def test_fourstep_paths_on_one_gpu(D, log_n):

@@ -109,3 +109,28 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("oracle/", "").lower() or f == "__init__.py" or "import oracle" not in text
                 assert "from oracle" not in text and "import oracle" not in text and "toyni_oracle" not in text, f
+
+
+def test_fast_shoup_companion_is_exact(tmp_path):
+    """bb_field.cuh::shoup_companion_fast (device-side twiddle generation of the warp-private pass kernels, no 64-bit
+    division) must equal floor(w 2^32 / p) for every canonical w: both ends of the range and 20 million random values."""
+    import subprocess
+    src = tmp_path / "t.cpp"
+    src.write_text(r"""
+#include "bb_field.cuh"
+#include <cstdio>
+#include <random>
+int main() {
+    std::mt19937_64 g(1);
+    unsigned long long bad = 0;
+    auto chk = [&](uint32_t w) { if (bb::shoup_companion_fast(w) != bb::shoup_companion(w)) bad++; };
+    for (uint32_t w = 0; w < 1000000; w++) chk(w);
+    for (uint32_t w = bb::P - 1000000; w < bb::P; w++) chk(w);
+    for (int i = 0; i < 20000000; i++) chk((uint32_t)(g() % bb::P));
+    printf("%llu\n", bad);
+    return bad != 0;
+}
+""")
+    exe = tmp_path / "t.bin"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "toyni_b200", "csrc"), str(src), "-o", str(exe)])
+    assert subprocess.check_output([str(exe)]).decode().strip() == "0"

@@ -11,6 +11,7 @@ from toyni_b200 import device as D
 from toyni_b200.lib import P, lib
 
 L = lib()
+MODE = int([a for a in sys.argv[1:] if a.isdigit()][0]) if any(a.isdigit() for a in sys.argv[1:]) else 1
 out = {"parity": [], "timing": []}
 
 
@@ -29,7 +30,7 @@ def parity(kind, shape, inverse):
     a, b = x.clone(), x.clone()
     L.bb_ntt_set_kernel(0, 0)
     run(kind, a, inverse)
-    L.bb_ntt_set_kernel(1, 0)
+    L.bb_ntt_set_kernel(MODE, 0)
     run(kind, b, inverse)
     torch.cuda.synchronize()
     ok = bool(torch.equal(a, b))
@@ -43,7 +44,7 @@ def timing(kind, shape, reps=200):
     nbuf = max(2, min(8, (1 << 28) // (4 * int(torch.tensor(shape).prod())) + 1))
     bufs = [torch.randint(0, P, shape, dtype=torch.int32, device="cuda") for _ in range(nbuf)]
     res = {"kind": kind, "shape": list(shape)}
-    for v5 in (0, 1):
+    for v5 in (0, MODE):
         L.bb_ntt_set_kernel(v5, 0)
         for i in range(5):
             run(kind, bufs[i % nbuf], False)

@@ -2,7 +2,7 @@
 #include "ntt_engine.cuh"
 
 #include "fri_fold.cuh"
-#include "ntt_pass_v5.cuh"
+#include "ntt_pass_v6.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -45,10 +45,10 @@ __global__ void gen_shoup_kernel(uint2* out, uint32_t count, uint32_t g_m) {
 
 // btab[e*8 + c] = Shoup pair of g^(c*e): the column-dependent factor of the first pass's inter-pass twiddle
 // (ntt_pass_v5.cuh)
-__global__ void gen_btab_kernel(uint2* out, uint32_t g_m) {
+__global__ void gen_btab_kernel(uint2* out, uint32_t g_m, uint32_t log_cols) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (uint32_t)(V5_R * 8)) {
-        uint32_t w = from_monty(monty_pow_dev(g_m, (i >> 3) * (i & 7u)));
+    if (i < ((uint32_t)V5_R << log_cols)) {
+        uint32_t w = from_monty(monty_pow_dev(g_m, (i >> log_cols) * (i & ((1u << log_cols) - 1u))));
         out[i] = make_uint2(w, shoup_companion(w));
     }
 }
@@ -56,6 +56,9 @@ __global__ void gen_btab_kernel(uint2* out, uint32_t g_m) {
 extern template int launch_pass_v5<V5_ROWS_CANON>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
 extern template int launch_pass_v5<V5_ROWS_TWIDDLE>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
 extern template int launch_pass_v5<V5_COLS_TWIDDLE>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
+extern template int launch_pass_v6<V5_ROWS_CANON>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
+extern template int launch_pass_v6<V5_ROWS_TWIDDLE>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
+extern template int launch_pass_v6<V5_COLS_TWIDDLE>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
 
 // ------------------------------------------------------------------ per-device state
 struct PowTab {
@@ -71,7 +74,7 @@ struct DeviceState {
     // one scratch buffer per stream: transforms on different streams (e.g. two legacy contexts used from two host
     // threads) may execute concurrently and must not share the intermediate array
     std::map<cudaStream_t, std::pair<uint32_t*, size_t>> scratch;
-    std::map<uint32_t, uint2*> btabs;  // g -> table of g^(c*e), c < 8, e < 256
+    std::map<std::pair<uint32_t, uint32_t>, uint2*> btabs;  // (g, log2 columns) -> table of g^(c*e), e < 256
     bool ready = false;
 };
 
@@ -79,6 +82,7 @@ static std::mutex g_mu;
 static std::map<int, DeviceState> g_states;
 static std::map<int, NttPlan> g_plan_override;
 static bool g_force_scalar = false;  // test hook: run every pass on the scalar kernel
+int g_pdl = 1;
 static int g_v5 = -1;                // warp-private kernel for R = 256 passes (TOYNI_NTT_V5=0 switches it off)
 static uint32_t g_v5_min_strips = 2048;
 
@@ -137,15 +141,17 @@ static int pow_table_get(DeviceState& st, uint32_t g, int log_total, uint32_t sc
     return 0;
 }
 
-static int btab_get(DeviceState& st, uint32_t g, const uint2** out) {
-    auto it = st.btabs.find(g);
+static int btab_get(DeviceState& st, uint32_t g, uint32_t log_cols, const uint2** out) {
+    auto key = std::make_pair(g, log_cols);
+    auto it = st.btabs.find(key);
     if (it == st.btabs.end()) {
         uint2* t = nullptr;
-        BB_CK(cudaMalloc(&t, sizeof(uint2) * V5_R * 8));
-        gen_btab_kernel<<<(V5_R * 8 + 255) / 256, 256>>>(t, to_monty(g));
+        const uint32_t cnt = (uint32_t)V5_R << log_cols;
+        BB_CK(cudaMalloc(&t, sizeof(uint2) * cnt));
+        gen_btab_kernel<<<(cnt + 255) / 256, 256>>>(t, to_monty(g), log_cols);
         BB_CK(cudaGetLastError());
         BB_CK(cudaDeviceSynchronize());
-        it = st.btabs.emplace(g, t).first;
+        it = st.btabs.emplace(key, t).first;
     }
     *out = it->second;
     return 0;
@@ -272,7 +278,7 @@ static NttPlan plan_locked(int log_n, int log_inner, size_t batch) {
 
 void engine_enable_v5(int on, uint32_t min_strips) {
     std::lock_guard<std::mutex> lk(g_mu);
-    g_v5 = on ? 1 : 0;
+    g_v5 = on;  // 0 tile kernel, 1 warp-private 8-column strips, 2 warp-private 16-column strips
     if (min_strips) g_v5_min_strips = min_strips;
 }
 
@@ -463,23 +469,39 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
         // warp-private kernel: full-length 256-point passes of large transforms (plain twiddle or no epilogue)
         if (g_v5 < 0) {
             const char* e = getenv("TOYNI_NTT_V5");
-            g_v5 = (e && e[0] == '0') ? 0 : 1;
+            g_v5 = e ? atoi(e) : 0;
+            const char* e2 = getenv("TOYNI_NTT_PDL");
+            if (e2) g_pdl = atoi(e2);
         }
         if (g_v5 && !g_force_scalar && !transposed && lr == V5_LR && aligned && p.pro_mode == PRO_NONE &&
             (!first || d.n_in == n) && (p.ncols % 32u) == 0 &&
             (size_t)(p.ncols / 8u) * d.batch >= g_v5_min_strips && (size_t)(p.ncols / 8u) * d.batch < (1ull << 31) &&
-            ((p.epi_mode == EPI_NONE && p.log_pfull >= 3) ||
-             (p.epi_mode == EPI_TWIDDLE && (p.log_pfull >= 3 || (p.log_pfull == 0 && d.log_inner == 0))))) {
-            const uint32_t strips_x = p.ncols / 8u;
-            if (p.epi_mode == EPI_NONE) {
-                rc = launch_pass_v5<V5_ROWS_CANON>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
-            } else if (p.log_pfull >= 3) {
-                rc = launch_pass_v5<V5_ROWS_TWIDDLE>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
+            ((p.epi_mode == EPI_NONE && p.log_pfull >= 4) ||
+             (p.epi_mode == EPI_TWIDDLE && (p.log_pfull >= 4 || (p.log_pfull == 0 && d.log_inner == 0))))) {
+            if (g_v5 == 2) {  // wide strips (16 columns)
+                const uint32_t strips_x = p.ncols / 16u;
+                if (p.epi_mode == EPI_NONE) {
+                    rc = launch_pass_v6<V5_ROWS_CANON>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
+                } else if (p.log_pfull >= 4) {
+                    rc = launch_pass_v6<V5_ROWS_TWIDDLE>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
+                } else {
+                    const uint2* btab = nullptr;
+                    rc = btab_get(*st, bb::pow(omega, 1ull << p.epi_shift), 4, &btab);
+                    if (rc) return rc;
+                    rc = launch_pass_v6<V5_COLS_TWIDDLE>(p, btab, strips_x, (uint32_t)d.batch, stream);
+                }
             } else {
-                const uint2* btab = nullptr;
-                rc = btab_get(*st, bb::pow(omega, 1ull << p.epi_shift), &btab);
-                if (rc) return rc;
-                rc = launch_pass_v5<V5_COLS_TWIDDLE>(p, btab, strips_x, (uint32_t)d.batch, stream);
+                const uint32_t strips_x = p.ncols / 8u;
+                if (p.epi_mode == EPI_NONE) {
+                    rc = launch_pass_v5<V5_ROWS_CANON>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
+                } else if (p.log_pfull >= 3) {
+                    rc = launch_pass_v5<V5_ROWS_TWIDDLE>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
+                } else {
+                    const uint2* btab = nullptr;
+                    rc = btab_get(*st, bb::pow(omega, 1ull << p.epi_shift), 3, &btab);
+                    if (rc) return rc;
+                    rc = launch_pass_v5<V5_COLS_TWIDDLE>(p, btab, strips_x, (uint32_t)d.batch, stream);
+                }
             }
             if (rc) return rc;
             log_p += lr;

@@ -379,6 +379,11 @@ __global__ void __launch_bounds__(V4<LR, LC>::NT) ntt_pass_v4_kernel(const PassP
     if constexpr (T::TW_BYTES > 0) {
         for (uint32_t i = tid; i < (uint32_t)(R / 2); i += NT) stw[i] = __ldg(&p.tw[i << (LOG_TW - LR)]);
     }
+    // Programmatic dependent launch: everything above ran while the previous kernel in the stream (the previous pass)
+    // was still draining; its output is only touched from here on.  The next kernel may be scheduled as soon as
+    // every CTA of this one has got this far (it waits for our completion at the same point).
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
     if (DB) {
         const uint32_t bz = tile / tiles_x, tx = tile - bz * tiles_x;
         load_tile_v4<LR, LC>(smv_all, p.in + (size_t)bz * p.in_batch_stride, p, tx * C);
@@ -475,6 +480,8 @@ __global__ void __launch_bounds__(V4<LR, LC>::NT) ntt_pass_v4_kernel(const PassP
     }
 }
 
+extern int g_pdl;  // ntt_engine.cu: programmatic dependent launch between passes (TOYNI_NTT_PDL=0 switches it off)
+
 template <int LR, int LC>
 void launch_pass_v4(const PassParams& p, dim3 grid, cudaStream_t s) {
     using T = V4<LR, LC>;
@@ -496,7 +503,17 @@ void launch_pass_v4(const PassParams& p, dim3 grid, cudaStream_t s) {
     const uint32_t tiles_x = grid.x, total = grid.x * grid.y;
     uint32_t ctas = (uint32_t)(ctas_per_sm[dev] * n_sm[dev]);
     if (ctas > total) ctas = total;
-    ntt_pass_v4_kernel<LR, LC, DB><<<ctas, T::NT, smem, s>>>(p, tiles_x, total);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(T::NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, ntt_pass_v4_kernel<LR, LC, DB>, p, tiles_x, total);
 }
 
 }  // namespace bb
