@@ -159,6 +159,27 @@ int bb_fri_commit_device(const uint32_t* d_layer0, size_t n, uint32_t shift, siz
                          const uint8_t* d_salts, bb_challenge_fn challenge, void* user, const uint32_t* betas_in,
                          uint32_t* d_layers, uint8_t* d_nodes, uint8_t* roots_out, size_t* folds_out);
 
+/* Openings of a whole query set in one launch (src/fibonacci.rs:250-295 over src/merkle.rs:50-80): `indices` (host)
+ * names nq leaves; paths_out (host) receives nq * depth * 32 bytes, pos_out nq * depth flags, *depth_out the depth.
+ * bb_gather_device fetches the opened values / salts: out[q] = src[indices[q]] for elements of elem_bytes bytes. */
+int bb_merkle_open_batch_device(const uint8_t* d_nodes, size_t nleaves, const uint64_t* indices, size_t nq, uint8_t* paths_out,
+                                uint8_t* pos_out, size_t* depth_out);
+int bb_gather_device(const void* d_src, size_t elem_bytes, const uint64_t* indices, size_t nq, void* out);
+
+/* Element-wise stages of StarkProver::generate_proof between the LDE and the FRI commit loop, device-resident
+ * (SURVEY 8f rank 1).  x_i = shift * w_N^i (N = 2^log_n) comes from the twiddle cache; `step` is the blowup, so that
+ * T(g x_i) = d_trace_lde[(i + step) mod N] (src/verifier.rs:128-129).
+ *   constraint: c[i] = (T(g^2 x) - T(g x) - T(x)) (x - b1) (x - b2)                     src/fibonacci.rs:133-143
+ *   scale_periodic: v[i] *= table[i mod period] (1 / Z_H(x_i) takes `blowup` values)      src/fibonacci.rs:147-150
+ *   deep: d[i] = ((Q - q_z) + (T(g^2 x) - t_ggz) + (T(g x) - t_gz) + (T(x) - t_z)) / (x_i - z)   src/fibonacci.rs:186-198
+ *   poly_eval: sum_k coeffs[k] z^k                                                       src/math/polynomial.rs:134-144 */
+int bb_fib_constraint_device(const uint32_t* d_trace_lde, uint32_t log_n, uint32_t step, uint32_t shift, uint32_t b1, uint32_t b2,
+                             uint32_t* d_out);
+int bb_scale_periodic_device(uint32_t* d_vals, size_t n, const uint32_t* table, uint32_t period);
+int bb_fib_deep_device(const uint32_t* d_quotient, const uint32_t* d_trace_lde, uint32_t log_n, uint32_t step, uint32_t shift, uint32_t z,
+                       uint32_t q_z, uint32_t t_z, uint32_t t_gz, uint32_t t_ggz, uint32_t* d_out);
+int bb_poly_eval_device(const uint32_t* d_coeffs, size_t n, uint32_t z, uint32_t* value_out);
+
 /* Tuning / introspection */
 int bb_ntt_set_plan(uint32_t log_n, int npass, const int* log_rows, const int* log_cols); /* npass 0 = default */
 int bb_ntt_get_plan(uint32_t log_n, int* log_rows, int* log_cols);                        /* returns npass */

@@ -270,17 +270,44 @@ def _verify_opening(o, root):  # src/verifier.rs:235-238
     return O.merkle_verify(leaf, path, np.array(o["position"], np.uint8), root)
 
 
-def verify(p):
-    """StarkVerifier::verify, src/verifier.rs:14-232."""
+class _CosetPoints:
+    """shifted_elements[i] = 7 w^i on demand (large proofs: the verifier reads 44 * O(log N) of the 32n points)."""
+
+    def __init__(self, lde):
+        self.w = O.root_of_unity(lde.bit_length() - 1)
+
+    def __getitem__(self, i):
+        return COSET_SHIFT * pow(self.w, int(i), P) % P
+
+
+def derive_z_algebraic(transcript, lde):
+    """derive_z without the two 32n-element sets: z is in the extended domain iff z^N = 1 and in the shifted domain
+    iff (z / 7)^N = 1; g_ext^k z is in the shifted domain iff z is.  Same z as src/fibonacci.rs:378-399."""
+    inv_shift = pow(COSET_SHIFT, P - 2, P)
+    while True:
+        z = transcript.squeeze_challenge()
+        if pow(z, lde, P) != 1 and pow(z * inv_shift % P, lde, P) != 1:
+            return z
+
+
+def verify(p, algebraic=None):
+    """StarkVerifier::verify, src/verifier.rs:14-232.  `algebraic` (default: for lde >= 2^21) swaps the materialised
+    domains for their closed forms; both ways give the same verdict (tests/test_oracle_reference_tests.py)."""
     n, lde = p["trace_len"], p["lde_size"]
     if lde != n * BLOWUP:
         return False
+    if algebraic is None:
+        algebraic = lde >= (1 << 21)
     g = O.root_of_unity(n.bit_length() - 1)
     g_ext = O.root_of_unity(lde.bit_length() - 1)
-    shifted = O.domain_elements(lde, COSET_SHIFT)
     tr = O.FiatShamirTranscript()
     tr.absorb(p["trace_commitment"]); tr.absorb(p["quotient_commitment"])
-    z = derive_z(tr, O.domain_elements(lde, 1), shifted, g_ext)
+    if algebraic:
+        shifted = _CosetPoints(lde)
+        z = derive_z_algebraic(tr, lde)
+    else:
+        shifted = O.domain_elements(lde, COSET_SHIFT)
+        z = derive_z(tr, O.domain_elements(lde, 1), shifted, g_ext)
     for k in ("t_z", "t_gz", "t_ggz", "q_z"):
         tr.absorb_field(p[k])
     c_z = (p["t_ggz"] - (p["t_gz"] + p["t_z"])) % P * ((z - pow(g, n - 1, P)) % P) % P * ((z - pow(g, n - 2, P)) % P) % P

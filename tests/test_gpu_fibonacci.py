@@ -41,6 +41,21 @@ def test_verifier_rejects_tampering_cpu():
         assert not F.verify(bad)
 
 
+def test_algebraic_verifier_agrees_with_the_literal_one_cpu():
+    """The closed-form domain membership / coset points used for large proofs give the same verdicts and the same z."""
+    from oracle import oracle as O
+    p = F.generate_proof(F.fibonacci_trace(64), *F.proof_randomness(64), interpolate="intt")
+    assert F.verify(p, algebraic=True) and F.verify(p, algebraic=False)
+    for bad in _tamper_cases(p):
+        assert not F.verify(bad, algebraic=True)
+    for seed in range(5):
+        t1, t2 = O.FiatShamirTranscript(), O.FiatShamirTranscript()
+        t1.absorb(bytes([seed]) * 32); t2.absorb(bytes([seed]) * 32)
+        lde = 2048
+        z1 = F.derive_z(t1, O.domain_elements(lde, 1), O.domain_elements(lde, F.COSET_SHIFT), O.root_of_unity(11))
+        assert z1 == F.derive_z_algebraic(t2, lde)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("trace_len", [64, 1 << 10])
 def test_gpu_proof_is_byte_identical_and_verifies(trace_len):
@@ -55,3 +70,25 @@ def test_gpu_proof_is_byte_identical_and_verifies(trace_len):
         assert got["lde_size"] == 32768 and len(got["fri_commitments"]) == 12 and len(got["fri_final_layer"]) == 16
     for bad in _tamper_cases(got):
         assert not F.verify(bad)
+
+
+@pytest.mark.gpu
+def test_gpu_proof_at_2_14_stays_on_the_device_and_verifies():
+    """Beyond the size the O(n^3) reference prover can reach: trace 2^14 (LDE 2^19), every LDE-sized array on the device
+    (constraint / quotient / DEEP kernels, batched openings), salts drawn on the device; the restated verifier accepts
+    and the tamper cases are rejected."""
+    import torch
+    from oracle import oracle as O
+    from toyni_b200 import prover
+    trace_len = 1 << 14
+    lde = trace_len * 32
+    tr = F.fibonacci_trace(trace_len)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    salts = [torch.randint(0, 256, (m, 16), dtype=torch.uint8, device="cuda", generator=g) for m in (lde, lde, 2 * lde)]
+    p = prover.generate_proof(tr, O.random_field(prover.MASK_DEGREE, 3), *salts)
+    assert p["lde_size"] == lde and len(p["query_proofs"]) == 44
+    assert F.verify(p, algebraic=False)
+    assert F.verify(p, algebraic=True)
+    for bad in _tamper_cases(p):
+        assert not F.verify(bad, algebraic=True)

@@ -10,6 +10,7 @@
 #include "fri_fold.cuh"
 #include "merkle.cuh"
 #include "ntt_engine.cuh"
+#include "prover_ew.cuh"
 
 using namespace bb;
 
@@ -337,6 +338,91 @@ int bb_merkle_open_device(const uint8_t* d_nodes, size_t nleaves, size_t index, 
     if (rc == 0) rc = (int)cudaStreamSynchronize(cur_stream());
     cudaFree(d_path);
     if (depth_out) *depth_out = depth;
+    return note(rc);
+}
+
+// ---- whole query sets at once (src/fibonacci.rs:250-295): paths, and the opened values / salts
+int bb_merkle_open_batch_device(const uint8_t* d_nodes, size_t nleaves, const uint64_t* indices, size_t nq, uint8_t* paths_out,
+                                uint8_t* pos_out, size_t* depth_out) {
+    size_t depth = 0;
+    for (size_t m = nleaves; m > 1; m = (m + 1) / 2) depth++;
+    if (depth_out) *depth_out = depth;
+    if (nq == 0) return 0;
+    for (size_t q = 0; q < nq; q++) {
+        if (indices[q] >= nleaves) return note((int)cudaErrorInvalidValue);
+        size_t level_n = nleaves, cur = (size_t)indices[q], d = 0;
+        while (level_n > 1) {  // position flags need no device data (src/merkle.rs:67-73)
+            size_t sib = (cur % 2 == 0) ? cur + 1 : cur - 1;
+            pos_out[q * depth + d++] = (sib >= level_n) ? 1 : (uint8_t)(cur % 2 == 1);
+            cur /= 2;
+            level_n = (level_n + 1) / 2;
+        }
+    }
+    if (depth == 0) return 0;
+    cudaStream_t s = cur_stream();
+    unsigned long long* d_idx = nullptr;
+    uint8_t* d_paths = nullptr;
+    CK(cudaMalloc(&d_idx, nq * sizeof(unsigned long long)));
+    int rc = (int)cudaMalloc(&d_paths, nq * depth * 32);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(d_idx, indices, nq * sizeof(unsigned long long), cudaMemcpyHostToDevice, s);
+    if (rc == 0) rc = merkle_gather_paths(d_nodes, nleaves, d_idx, nq, (uint32_t)depth, d_paths, s);
+    if (rc == 0) {
+        g_launches++;
+        rc = (int)cudaMemcpyAsync(paths_out, d_paths, nq * depth * 32, cudaMemcpyDeviceToHost, s);
+    }
+    if (rc == 0) rc = (int)cudaStreamSynchronize(s);
+    cudaFree(d_idx);
+    cudaFree(d_paths);
+    return note(rc);
+}
+int bb_gather_device(const void* d_src, size_t elem_bytes, const uint64_t* indices, size_t nq, void* out) {
+    if (nq == 0 || elem_bytes == 0) return 0;
+    cudaStream_t s = cur_stream();
+    unsigned long long* d_idx = nullptr;
+    uint8_t* d_out = nullptr;
+    CK(cudaMalloc(&d_idx, nq * sizeof(unsigned long long)));
+    int rc = (int)cudaMalloc(&d_out, nq * elem_bytes);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(d_idx, indices, nq * sizeof(unsigned long long), cudaMemcpyHostToDevice, s);
+    if (rc == 0) rc = gather_elems(d_src, (uint32_t)elem_bytes, d_idx, nq, d_out, s);
+    if (rc == 0) {
+        g_launches++;
+        rc = (int)cudaMemcpyAsync(out, d_out, nq * elem_bytes, cudaMemcpyDeviceToHost, s);
+    }
+    if (rc == 0) rc = (int)cudaStreamSynchronize(s);
+    cudaFree(d_idx);
+    cudaFree(d_out);
+    return note(rc);
+}
+
+// ---- element-wise stages of the Fibonacci prover between the LDE and the FRI commit loop
+int bb_fib_constraint_device(const uint32_t* d_trace_lde, uint32_t log_n, uint32_t step, uint32_t shift, uint32_t b1, uint32_t b2,
+                             uint32_t* d_out) {
+    CK(fib_constraint(d_trace_lde, d_out, (int)log_n, step, shift, b1, b2, cur_stream()));
+    g_launches++;
+    return 0;
+}
+int bb_scale_periodic_device(uint32_t* d_vals, size_t n, const uint32_t* table, uint32_t period) {
+    CK(scale_periodic(d_vals, n, table, period, cur_stream()));
+    g_launches++;
+    return 0;
+}
+int bb_fib_deep_device(const uint32_t* d_quotient, const uint32_t* d_trace_lde, uint32_t log_n, uint32_t step, uint32_t shift, uint32_t z,
+                       uint32_t q_z, uint32_t t_z, uint32_t t_gz, uint32_t t_ggz, uint32_t* d_out) {
+    CK(fib_deep(d_quotient, d_trace_lde, d_out, (int)log_n, step, shift, z, q_z, t_z, t_gz, t_ggz, cur_stream()));
+    g_launches++;
+    return 0;
+}
+int bb_poly_eval_device(const uint32_t* d_coeffs, size_t n, uint32_t z, uint32_t* value_out) {
+    cudaStream_t s = cur_stream();
+    unsigned long long* d_acc = nullptr;
+    unsigned long long h = 0;
+    CK(cudaMalloc(&d_acc, sizeof(unsigned long long)));
+    int rc = poly_eval(d_coeffs, n, z, d_acc, s);
+    if (rc == 0) rc = (int)cudaMemcpyAsync(&h, d_acc, sizeof h, cudaMemcpyDeviceToHost, s);
+    if (rc == 0) rc = (int)cudaStreamSynchronize(s);
+    cudaFree(d_acc);
+    g_launches++;
+    if (rc == 0 && value_out) *value_out = (uint32_t)(h % (unsigned long long)P);
     return note(rc);
 }
 

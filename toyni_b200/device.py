@@ -142,6 +142,70 @@ def merkle_commit(vals, salts=None, nodes=None, want_root=True):
     return nodes, (root.tobytes() if want_root else None)
 
 
+def merkle_open_batch(nodes, nleaves, indices):
+    """Authentication paths of a whole query set in one launch (src/merkle.rs:50-80 for every index).
+    Returns (paths uint8 [nq, depth, 32], positions uint8 [nq, depth])."""
+    _bind_stream()
+    idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64))
+    depth = C.c_size_t(0)
+    d = max(int(nleaves) - 1, 0).bit_length()
+    paths = np.zeros((idx.size, d, 32), dtype=np.uint8)
+    pos = np.zeros((idx.size, d), dtype=np.uint8)
+    check(lib().bb_merkle_open_batch_device(C.c_void_p(nodes.data_ptr()), nleaves, idx.ctypes.data, idx.size, paths.ctypes.data,
+                                            pos.ctypes.data, C.byref(depth)), "bb_merkle_open_batch_device")
+    assert depth.value == d
+    return paths, pos
+
+
+def gather(t, indices):
+    """Rows t[indices] of a contiguous device tensor, fetched with one kernel and one copy."""
+    _bind_stream()
+    assert t.is_cuda and t.is_contiguous()
+    idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64))
+    row = t[0].numel() * t.element_size() if t.dim() > 1 else t.element_size()
+    out = np.zeros((idx.size, row), dtype=np.uint8)
+    check(lib().bb_gather_device(C.c_void_p(t.data_ptr()), row, idx.ctypes.data, idx.size, out.ctypes.data), "bb_gather_device")
+    return out
+
+
+def fib_constraint(trace_lde, step, shift, b1, b2, out=None):
+    """src/fibonacci.rs:133-143 over the whole shifted domain: (T(g^2 x) - T(g x) - T(x)) (x - b1) (x - b2)."""
+    _bind_stream()
+    n = trace_lde.numel()
+    if out is None:
+        out = torch.empty_like(trace_lde)
+    check(lib().bb_fib_constraint_device(_chk(trace_lde), n.bit_length() - 1, step, shift % P, b1 % P, b2 % P, _chk(out)),
+          "bb_fib_constraint_device")
+    return out
+
+
+def scale_periodic_(vals, table):
+    """vals[i] *= table[i mod len(table)] in place (len a power of two <= 64)."""
+    _bind_stream()
+    tab = np.ascontiguousarray(np.asarray([int(v) % P for v in table], dtype=np.uint32))
+    check(lib().bb_scale_periodic_device(_chk(vals), vals.numel(), tab.ctypes.data, tab.size), "bb_scale_periodic_device")
+    return vals
+
+
+def fib_deep(quotient, trace_lde, step, shift, z, q_z, t_z, t_gz, t_ggz, out=None):
+    """DEEP composition polynomial over the shifted domain (src/fibonacci.rs:186-198), 1/(x - z) by batched inversion."""
+    _bind_stream()
+    n = trace_lde.numel()
+    if out is None:
+        out = torch.empty_like(trace_lde)
+    check(lib().bb_fib_deep_device(_chk(quotient), _chk(trace_lde), n.bit_length() - 1, step, shift % P, z % P, q_z % P, t_z % P,
+                                   t_gz % P, t_ggz % P, _chk(out)), "bb_fib_deep_device")
+    return out
+
+
+def poly_eval(coeffs, z):
+    """Polynomial::evaluate (src/math/polynomial.rs:134-144) of device-resident coefficients at one point."""
+    _bind_stream()
+    v = C.c_uint32(0)
+    check(lib().bb_poly_eval_device(_chk(coeffs), coeffs.numel(), int(z) % P, C.byref(v)), "bb_poly_eval_device")
+    return int(v.value)
+
+
 def fri_commit(layer0, shift, final_size, salts=None, challenge=None, betas=None, hash_layers=True):
     """The prover's FRI commit loop (src/fibonacci.rs:200-247) on device-resident data.
     challenge(root: bytes, layer: int) -> beta (int or 4 limbs) plays the transcript; alternatively

@@ -4,8 +4,10 @@ What runs on the device (through the C ABI): the trace interpolation (coset-free
 blowup-32 coset LDE of the masked trace polynomial (NTT instead of the reference's per-point Horner,
 src/fibonacci.rs:124-128 — same values, the arithmetic is exact), both coset IFFTs (:145,151), every salted /
 unsalted Merkle tree (:129,153,206,234-238) and the FRI commit loop (:200-247) with the transcript as its callback.
-What stays on the host: the Fiat-Shamir transcript, the constraint / quotient / DEEP element-wise formulas
-(numpy), out-of-domain evaluations and the query openings — serial protocol code, out of scope.
+the constraint / quotient / DEEP element-wise formulas (closed forms over the coset, batched
+inversion), the out-of-domain evaluations and the openings of the whole query set (rank 3).
+What stays on the host: the Fiat-Shamir transcript, the trace_len + 140 coefficients of the masked trace polynomial
+and the assembly of the proof object — serial protocol code, out of scope.
 
 The reference draws blinding from thread_rng(); here mask coefficients and salts are explicit inputs so that a proof
 is reproducible (and comparable byte for byte with the CPU oracle's)."""
@@ -52,8 +54,6 @@ class FiatShamirTranscript:
         return out
 
 
-def _mul(a, b):
-    return (np.asarray(a, np.uint64) * np.asarray(b, np.uint64)) % _P
 
 
 def _add(a, b):
@@ -64,15 +64,6 @@ def _sub(a, b):
     return (np.asarray(a, np.uint64) + _P - np.asarray(b, np.uint64)) % _P
 
 
-def _pow(a, e):
-    a = np.asarray(a, np.uint64)
-    r = np.ones_like(a)
-    while e:
-        if e & 1:
-            r = _mul(r, a)
-        a = _mul(a, a)
-        e >>= 1
-    return r
 
 
 def _trim(c):  # Polynomial::new, src/math/polynomial.rs:11-16
@@ -82,101 +73,83 @@ def _trim(c):  # Polynomial::new, src/math/polynomial.rs:11-16
     return c[:n]
 
 
-def _horner(c, x):  # src/math/polynomial.rs:134-144
-    acc = 0
-    for v in reversed([int(t) for t in c]):
-        acc = (acc * x + v) % P
-    return acc
 
 
 class _Tree:
-    """A committed layer: device values + device nodes, host copies made lazily for the openings."""
+    """A committed layer: device values + device nodes; openings are gathered on the device (one launch per query
+    set), nothing but the opened paths, values and salts ever crosses PCIe."""
 
-    def __init__(self, vals_dev, nodes_dev, root, salts_host):
-        self.vals_dev, self.nodes_dev, self.root, self.salts = vals_dev, nodes_dev, root, salts_host
+    def __init__(self, vals_dev, nodes_dev, root, salts_dev):
+        self.vals_dev, self.nodes_dev, self.root, self.salts_dev = vals_dev, nodes_dev, root, salts_dev
         self.n = vals_dev.shape[0]
-        self._vals = self._nodes = None
 
-    def open(self, index):  # open_merkle, src/fibonacci.rs:366-374 + MerkleTree::get_proof, src/merkle.rs:50-80
-        if self._vals is None:
-            self._vals = D.to_host(self.vals_dev)
-            self._nodes = self.nodes_dev.cpu().numpy()
-        path, position, cur, off, n = [], [], index, 0, self.n
-        while n > 1:
-            sib = cur + 1 if cur % 2 == 0 else cur - 1
-            if sib >= n:
-                path.append(self._nodes[off + cur].tobytes())
-                position.append(True)
-            else:
-                path.append(self._nodes[off + sib].tobytes())
-                position.append(cur % 2 == 1)
-            cur //= 2
-            off += n
-            n = (n + 1) // 2
-        return {"index": int(index), "value": int(self._vals[index]), "path": path, "position": position,
-                "salt": b"" if self.salts is None else bytes(self.salts[index])}
+    def open_many(self, indices):  # open_merkle, src/fibonacci.rs:366-374 + MerkleTree::get_proof, src/merkle.rs:50-80
+        indices = [int(i) for i in indices]
+        paths, pos = D.merkle_open_batch(self.nodes_dev, self.n, indices)
+        vals = D.gather(self.vals_dev, indices).view(np.uint32).reshape(-1)
+        salts = None if self.salts_dev is None else D.gather(self.salts_dev, indices)
+        return [{"index": idx, "value": int(vals[k]), "path": [paths[k, d].tobytes() for d in range(paths.shape[1])],
+                 "position": [bool(b) for b in pos[k]], "salt": b"" if salts is None else salts[k].tobytes()}
+                for k, idx in enumerate(indices)]
+
+
+def _as_salts(s, device):
+    if isinstance(s, torch.Tensor):
+        return s.to(device).contiguous().view(-1, 16)
+    return torch.from_numpy(np.ascontiguousarray(s, np.uint8).reshape(-1, 16)).to(device)
 
 
 def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, device="cuda"):
+    """Every array of LDE size stays on the device: LDE, constraint / quotient / DEEP formulas, commits, FRI commit
+    loop and openings.  Salts may be numpy arrays or CUDA uint8 tensors."""
     trace_len = len(trace_column)
     lde = trace_len * BLOWUP
     g = get_root_of_unity(trace_len.bit_length() - 1)
-    g_ext = get_root_of_unity(lde.bit_length() - 1)
-    salts_trace = np.ascontiguousarray(salts_trace, np.uint8).reshape(lde, 16)
-    salts_quot = np.ascontiguousarray(salts_quot, np.uint8).reshape(lde, 16)
-    salts_fri = np.ascontiguousarray(salts_fri, np.uint8).reshape(-1)
+    salts_trace, salts_quot = _as_salts(salts_trace, device), _as_salts(salts_quot, device)
+    salts_fri = _as_salts(salts_fri, device)
 
-    # 1. trace polynomial (INTT on the GPU) + masking T + Z_H * R (:110-121)
+    # 1. trace polynomial (INTT on the GPU) + masking T + Z_H * R (:110-121): trace_len + 140 coefficients, host
     coeffs = _trim(D.to_host(D.coset_ifft_(D.to_device(np.asarray(trace_column, np.uint64), device), 1)))
     tp = np.zeros(trace_len + MASK_DEGREE, np.uint64)
     tp[:coeffs.size] = coeffs
     zr = np.zeros(trace_len + MASK_DEGREE, np.uint64)
     zr[trace_len:] = mask
     zr[:MASK_DEGREE] = _sub(zr[:MASK_DEGREE], mask)
-    trace_poly = _trim(_add(tp, zr))
-    # LDE on the shifted domain + commit (:124-130), all on the device
-    shifted_dev = D.coset_fft(D.to_device(np.array([0, 1], np.uint64), device), lde, COSET_SHIFT)  # the coset itself
-    trace_lde_dev = D.coset_fft(D.to_device(trace_poly, device), lde, COSET_SHIFT)
-    nodes, root = D.merkle_commit(trace_lde_dev, torch.from_numpy(salts_trace).to(device))
+    trace_poly_dev = D.to_device(_trim(_add(tp, zr)), device)
+    # LDE on the shifted domain + commit (:124-130)
+    trace_lde_dev = D.coset_fft(trace_poly_dev, lde, COSET_SHIFT)
+    nodes, root = D.merkle_commit(trace_lde_dev, salts_trace)
     trace_tree = _Tree(trace_lde_dev, nodes, root, salts_trace)
-    # 2. constraint and quotient (:133-153): element-wise on the host, both IFFTs on the device
-    xs = D.to_host(shifted_dev)
-    t_x = D.to_host(trace_lde_dev)
-    t_gx, t_ggx = np.roll(t_x, -BLOWUP), np.roll(t_x, -2 * BLOWUP)  # T(g x_i) = trace_lde[(i + 32) % N]
-    b1 = _sub(xs, np.uint64(pow(g, trace_len - 1, P)))
-    b2 = _sub(xs, np.uint64(pow(g, trace_len - 2, P)))
-    c_evals = _mul(_mul(_sub(t_ggx, _add(t_gx, t_x)), b1), b2)
-    c_poly = _trim(D.to_host(D.coset_ifft_(D.to_device(c_evals, device), COSET_SHIFT)))
-    c_on_domain = D.to_host(D.coset_fft(D.to_device(c_poly, device), lde, COSET_SHIFT))  # c_poly.evaluate(x)
-    q_evals = _mul(c_on_domain, _pow(_sub(_pow(xs, trace_len), np.uint64(1)), P - 2))
-    q_dev = D.to_device(q_evals, device)
-    q_poly = _trim(D.to_host(D.coset_ifft_(q_dev.clone(), COSET_SHIFT)))
-    nodes, root = D.merkle_commit(q_dev, torch.from_numpy(salts_quot).to(device))
+    # 2. constraint and quotient (:133-153).  c_poly.evaluate(x) over the coset is c_evals itself (interpolate, then
+    #    evaluate at the same points), and Z_H(x_i) = 7^n (w_N^n)^i - 1 takes BLOWUP values.
+    c_dev = D.fib_constraint(trace_lde_dev, BLOWUP, COSET_SHIFT, pow(g, trace_len - 1, P), pow(g, trace_len - 2, P))
+    g_ext = get_root_of_unity(lde.bit_length() - 1)
+    sn, wn = pow(COSET_SHIFT, trace_len, P), pow(g_ext, trace_len, P)
+    q_dev = D.scale_periodic_(c_dev, [pow((sn * pow(wn, i, P) - 1) % P, P - 2, P) for i in range(BLOWUP)])
+    q_coeffs_dev = D.coset_ifft_(q_dev.clone(), COSET_SHIFT)
+    nodes, root = D.merkle_commit(q_dev, salts_quot)
     quot_tree = _Tree(q_dev, nodes, root, salts_quot)
-    # 3. Fiat-Shamir: z outside both domains (:156-161, :378-399)
+    # 3. Fiat-Shamir: z outside both domains (:156-161, :378-399).  Membership without building the 2 x 32n-element
+    #    sets: z is in the extended domain iff z^N = 1, in the shifted domain iff (z / 7)^N = 1, and g_ext^k z is in the
+    #    shifted domain iff z is (g_ext generates the extended domain).
     tr = FiatShamirTranscript()
     tr.absorb(trace_tree.root)
     tr.absorb(quot_tree.root)
-    ext_set = set(int(v) for v in D.to_host(D.coset_fft(D.to_device(np.array([0, 1], np.uint64), device), lde, 1)))
-    shift_set = set(int(v) for v in xs)
+    inv_shift = pow(COSET_SHIFT, P - 2, P)
     while True:
         z = tr.squeeze_challenge()
-        if (z not in ext_set and z not in shift_set and g_ext * z % P not in shift_set
-                and g_ext * g_ext % P * z % P not in shift_set):
+        if pow(z, lde, P) != 1 and pow(z * inv_shift % P, lde, P) != 1:
             break
     # 4. OOD evaluations (:164-183)
-    t_z, t_gz, t_ggz = _horner(trace_poly, z), _horner(trace_poly, g * z % P), _horner(trace_poly, g * g % P * z % P)
-    q_z = _horner(q_poly, z)
+    t_z, t_gz = D.poly_eval(trace_poly_dev, z), D.poly_eval(trace_poly_dev, g * z % P)
+    t_ggz, q_z = D.poly_eval(trace_poly_dev, g * g % P * z % P), D.poly_eval(q_coeffs_dev, z)
+    del q_coeffs_dev
     c_z = (t_ggz - (t_gz + t_z)) % P * ((z - pow(g, trace_len - 1, P)) % P) % P * ((z - pow(g, trace_len - 2, P)) % P) % P
     assert c_z == q_z * ((pow(z, trace_len, P) - 1) % P) % P, "Constraint check at z failed"  # :173-177
     for v in (t_z, t_gz, t_ggz, q_z):
         tr.absorb_field(v)
     # 5. DEEP polynomial (:186-198)
-    inv_xz = _pow(_sub(xs, np.uint64(z)), P - 2)
-    d_evals = _mul(_sub(q_evals, np.uint64(q_z)), inv_xz)
-    d_evals = _add(d_evals, _mul(_sub(t_ggx, np.uint64(t_ggz)), inv_xz))
-    d_evals = _add(d_evals, _mul(_sub(t_gx, np.uint64(t_gz)), inv_xz))
-    d_evals = _add(d_evals, _mul(_sub(t_x, np.uint64(t_z)), inv_xz))
+    d_dev = D.fib_deep(q_dev, trace_lde_dev, BLOWUP, COSET_SHIFT, z, q_z, t_z, t_gz, t_ggz)
     # 6. FRI commit loop on the device, transcript as the callback (:200-247)
     bound = 1 << (trace_len + MASK_DEGREE - 1).bit_length()
     final_size = lde // bound
@@ -185,31 +158,31 @@ def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, devic
         tr.absorb(root)
         return tr.squeeze_challenge()
 
-    layers, nodes_l, roots = D.fri_commit(D.to_device(d_evals, device), COSET_SHIFT, final_size,
-                                          torch.from_numpy(salts_fri).to(device), challenge=challenge)
+    layers, nodes_l, roots = D.fri_commit(d_dev, COSET_SHIFT, final_size, salts_fri.view(-1), challenge=challenge)
     tr.absorb(roots[-1])  # the callback absorbed every root but the last (no fold follows it), :239-242
     trees, off = [], 0
     for k, (lay, nd) in enumerate(zip(layers, nodes_l)):
         s = None
         if k < len(layers) - 1:
-            s = salts_fri[16 * off:16 * (off + lay.shape[0])].reshape(-1, 16)
+            s = salts_fri[off:off + lay.shape[0]]
             off += lay.shape[0]
         trees.append(_Tree(lay, nd, roots[k], s))
-    # 7. query phase (:250-295)
+    # 7. query phase (:250-295): one batched opening per tree
     queries = tr.squeeze_indices(NUM_QUERIES, lde // 2)
+    deep = trees[0].open_many([i for qi in queries for i in (qi, qi + lde // 2)])
+    trc = trace_tree.open_many([i for qi in queries for i in (qi, (qi + BLOWUP) % lde, (qi + 2 * BLOWUP) % lde)])
+    quo = quot_tree.open_many(queries)
+    fri, idxs = [], list(queries)
+    for k in range(1, len(trees) - 1):
+        half = trees[k].n // 2
+        idxs = [i % half for i in idxs]
+        fri.append(trees[k].open_many([j for i in idxs for j in (i, i + half)]))
     qps = []
-    for qi in queries:
-        qp = {"index": qi,
-              "deep_opening": trees[0].open(qi), "deep_opening_pair": trees[0].open(qi + lde // 2),
-              "trace_opening": trace_tree.open(qi), "trace_opening_g": trace_tree.open((qi + BLOWUP) % lde),
-              "trace_opening_gg": trace_tree.open((qi + 2 * BLOWUP) % lde), "quotient_opening": quot_tree.open(qi),
-              "fri_openings": []}
-        idx = qi
-        for k in range(1, len(trees) - 1):
-            half = trees[k].n // 2
-            idx %= half
-            qp["fri_openings"].append((trees[k].open(idx), trees[k].open(idx + half)))
-        qps.append(qp)
+    for n_q, qi in enumerate(queries):
+        qps.append({"index": qi, "deep_opening": deep[2 * n_q], "deep_opening_pair": deep[2 * n_q + 1],
+                    "trace_opening": trc[3 * n_q], "trace_opening_g": trc[3 * n_q + 1], "trace_opening_gg": trc[3 * n_q + 2],
+                    "quotient_opening": quo[n_q],
+                    "fri_openings": [(f[2 * n_q], f[2 * n_q + 1]) for f in fri]})
     return {"trace_len": trace_len, "lde_size": lde, "trace_commitment": trace_tree.root,
             "quotient_commitment": quot_tree.root, "t_z": t_z, "t_gz": t_gz, "t_ggz": t_ggz, "q_z": q_z,
             "fri_commitments": roots, "fri_final_layer": [int(v) for v in D.to_host(layers[-1])], "query_proofs": qps}
