@@ -166,6 +166,10 @@ int bb_merkle_open_batch_device(const uint8_t* d_nodes, size_t nleaves, const ui
                                 uint8_t* pos_out, size_t* depth_out);
 int bb_gather_device(const void* d_src, size_t elem_bytes, const uint64_t* indices, size_t nq, void* out);
 
+/* Re-layout after the cyclic -> block exchange of the sharded FRI commit (one process per GPU): d_src holds `groups`
+ * runs of `chunk` elements (limbs = 1 or 4 words each), run r supplying destination positions r, r + groups, ... */
+int bb_interleave_device(const uint32_t* d_src, uint32_t groups, size_t chunk, int limbs, uint32_t* d_dst);
+
 /* Element-wise stages of StarkProver::generate_proof between the LDE and the FRI commit loop, device-resident
  * (SURVEY 8f rank 1).  x_i = shift * w_N^i (N = 2^log_n) comes from the twiddle cache; `step` is the blowup, so that
  * T(g x_i) = d_trace_lde[(i + step) mod N] (src/verifier.rs:128-129).

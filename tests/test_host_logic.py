@@ -90,6 +90,74 @@ def test_fourstep_all_to_all_with_gloo_world_size_2(tmp_path):
     assert "gloo fourstep ok" in out.stdout
 
 
+_GLOO_COMMIT_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from oracle import oracle as O
+from toyni_b200 import multigpu as MG
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+log_m, final_size, shift = 12, 16, 7
+m = 1 << log_m
+layer0 = O.random_field(m, seed=11)
+nsalt, mm = 0, m
+while mm > final_size:
+    nsalt += mm; mm //= 2
+salts = O.random_bytes(16 * nsalt, seed=12).reshape(-1, 16)
+ref_layers, ref_roots, ref_betas = O.fri_commit(layer0, shift, final_size, salts.reshape(-1))
+
+class OracleBackend:                       # the same loop with the CPU oracle's primitives instead of the CUDA kernels
+    def __init__(self): self.t = O.FiatShamirTranscript()
+    def fold(self, local, log_mk, x0, beta, world, rank):
+        a = local.numpy().astype(np.uint64); half = a.size // 2
+        idx = rank + world * np.arange(half)
+        w = O.root_of_unity(log_mk)
+        xs = np.array([x0 * pow(w, int(i), O.P) % O.P for i in idx], np.uint64)
+        return torch.from_numpy(O.fri_fold(a, xs, beta).astype(np.int64))
+    def commit(self, vals, s):
+        nodes, root = O.commit_values(vals.numpy().astype(np.uint64), None if s is None else s.numpy())
+        return nodes, root
+    def finish(self, full, x0, final_size, s, challenge):
+        layers, roots, _ = O.fri_commit(full.numpy().astype(np.uint64), x0, final_size,
+                                        np.zeros(0, np.uint8) if s is None else s.numpy(), transcript=self.t)
+        return layers, None, roots
+    def bytes_tensor(self, b): return torch.frombuffer(bytearray(b), dtype=torch.uint8)
+
+B = OracleBackend()
+offs, o, mm = [], 0, m
+while mm > final_size:
+    offs.append(o); o += mm; mm //= 2
+def salts_for(k, lo, hi): return torch.from_numpy(salts[offs[k] + lo: offs[k] + hi].copy())
+def challenge(root, k):
+    B.t.absorb(root); return B.t.squeeze_challenge()
+local0 = torch.from_numpy(layer0[rank::world].astype(np.int64))
+roots, layers, nodes, tail = MG.fri_commit_sharded(local0, log_m, shift, final_size, salts_for, challenge, rank, world, B,
+                                                   gather_below=1 << 8)
+assert roots == ref_roots, "rank %d: roots differ" % rank
+assert np.array_equal(np.asarray(tail[-1], np.uint64), ref_layers[-1])
+for k, lay in enumerate(layers):           # every sharded layer is the cyclic shard of the reference layer
+    assert np.array_equal(lay.numpy().astype(np.uint64), ref_layers[k][rank::world])
+dist.barrier()
+if rank == 0: print("gloo sharded commit ok", len(roots), len(layers))
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_fri_commit_with_gloo_world_size_2(tmp_path):
+    """The multi-GPU FRI commit loop (cyclic fold shards, cyclic -> block exchange per layer, per-rank subtrees, top of
+    the tree on every rank) with a 2-rank gloo group and the oracle's primitives: same roots and layers as the
+    single-process loop of src/fibonacci.rs:200-247."""
+    script = tmp_path / "gloo_commit.py"
+    script.write_text(_GLOO_COMMIT_SCRIPT.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "gloo sharded commit ok" in out.stdout
+
+
 def test_product_path_refuses_to_run_without_a_device():
     import torch
     if torch.cuda.is_available():

@@ -297,13 +297,13 @@ int bb_fri_fold_xs_device(const uint32_t* d_evals, size_t m, const uint32_t* d_x
 
 size_t bb_merkle_node_count(size_t nleaves) { return merkle_node_count(nleaves); }
 
-static int levels_of(size_t n) {
+static int levels_of(size_t n) {  // kernel launches of merkle_upper_levels: one per level above 2048 nodes, one for the rest
     int l = 0;
-    while (n > 1) {
+    while (n > 2048) {
         n = (n + 1) / 2;
         l++;
     }
-    return l;
+    return l + (n > 1 ? 1 : 0);
 }
 
 static int root_to_host(const uint8_t* d_nodes, size_t n, uint8_t* root_out, cudaStream_t s) {
@@ -392,6 +392,13 @@ int bb_gather_device(const void* d_src, size_t elem_bytes, const uint64_t* indic
     cudaFree(d_idx);
     cudaFree(d_out);
     return note(rc);
+}
+
+int bb_interleave_device(const uint32_t* d_src, uint32_t groups, size_t chunk, int limbs, uint32_t* d_dst) {
+    if (groups == 0 || (limbs != 1 && limbs != 4)) return note((int)cudaErrorInvalidValue);
+    CK(interleave(d_src, d_dst, groups, chunk, (uint32_t)limbs, cur_stream()));
+    g_launches++;
+    return 0;
 }
 
 // ---- element-wise stages of the Fibonacci prover between the LDE and the FRI commit loop

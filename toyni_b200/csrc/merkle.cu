@@ -33,10 +33,7 @@ __global__ void __launch_bounds__(256) leaf_hash_kernel(const uint32_t* __restri
 }
 
 // Parent level: node j = SHA256(0x01 || child[2j] || child[2j+1]); an odd level pairs the last child with itself.
-__global__ void __launch_bounds__(256) node_hash_kernel(const uint8_t* __restrict__ child, uint8_t* __restrict__ parent,
-                                                        size_t n_child, size_t n_parent) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_parent) return;
+__device__ __forceinline__ void node_hash_one(const uint8_t* __restrict__ child, uint8_t* __restrict__ parent, size_t n_child, size_t j) {
     size_t li = 2 * j, ri = (2 * j + 1 < n_child) ? 2 * j + 1 : 2 * j;
     const uint4* L = reinterpret_cast<const uint4*>(child + 32 * li);
     const uint4* R = reinterpret_cast<const uint4*>(child + 32 * ri);
@@ -60,6 +57,28 @@ __global__ void __launch_bounds__(256) node_hash_kernel(const uint8_t* __restric
     w[15] = 65 * 8;
     sha_compress(s, w);
     store_digest(parent + 32 * j, s);
+}
+
+__global__ void __launch_bounds__(256) node_hash_kernel(const uint8_t* __restrict__ child, uint8_t* __restrict__ parent,
+                                                        size_t n_child, size_t n_parent) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_parent) return;
+    node_hash_one(child, parent, n_child, j);
+}
+
+// Every remaining level of a small tree (n_child <= 2 * TAIL_THREADS) in ONE launch: a single CTA walks the levels
+// with a barrier between them.  The late FRI layers (and the top of every tree) are launch bound otherwise: one
+// kernel per level, 13 levels for 2^13 leaves.
+constexpr int TAIL_THREADS = 1024;
+__global__ void __launch_bounds__(TAIL_THREADS) node_hash_tail_kernel(uint8_t* __restrict__ level, size_t n_child) {
+    while (n_child > 1) {
+        uint8_t* parent = level + 32 * n_child;
+        const size_t n_parent = (n_child + 1) / 2;
+        if (threadIdx.x < n_parent) node_hash_one(level, parent, n_child, threadIdx.x);
+        __syncthreads();  // block-scope ordering of the global stores above with the loads of the next level
+        level = parent;
+        n_child = n_parent;
+    }
 }
 
 // Generic leaves of arbitrary length (MerkleTree::new over raw byte strings)
@@ -131,13 +150,14 @@ size_t merkle_node_count(size_t nleaves) {
 int merkle_upper_levels(uint8_t* d_nodes, size_t n, cudaStream_t s) {
     uint8_t* cur = d_nodes;
     size_t cur_n = n;
-    while (cur_n > 1) {
+    while (cur_n > (size_t)2 * TAIL_THREADS) {
         uint8_t* next = cur + 32 * cur_n;
         size_t next_n = (cur_n + 1) / 2;
         node_hash_kernel<<<(unsigned)((next_n + 255) / 256), 256, 0, s>>>(cur, next, cur_n, next_n);
         cur = next;
         cur_n = next_n;
     }
+    if (cur_n > 1) node_hash_tail_kernel<<<1, TAIL_THREADS, 0, s>>>(cur, cur_n);
     return (int)cudaGetLastError();
 }
 

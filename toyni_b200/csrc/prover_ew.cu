@@ -116,7 +116,22 @@ __global__ void gather_elems_kernel(const uint8_t* __restrict__ src, uint32_t el
         out[(size_t)blockIdx.x * elem_bytes + b] = src[(size_t)idx[blockIdx.x] * elem_bytes + b];
 }
 
+// dst[(j*G + r)] = src[r*c + j], elements of `limbs` words (re-layout after the cyclic -> block exchange)
+__global__ void __launch_bounds__(256) interleave_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t groups,
+                                                         size_t chunk, uint32_t limbs) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // destination element
+    if (i >= (size_t)groups * chunk) return;
+    const size_t j = i / groups, r = i - j * groups;
+    for (uint32_t l = 0; l < limbs; l++) dst[i * limbs + l] = src[(r * chunk + j) * limbs + l];
+}
+
 // ---------------------------------------------------------------- host-side launchers
+int interleave(const uint32_t* d_src, uint32_t* d_dst, uint32_t groups, size_t chunk, uint32_t limbs, cudaStream_t s) {
+    const size_t n = (size_t)groups * chunk;
+    if (n) interleave_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_src, d_dst, groups, chunk, limbs);
+    return (int)cudaGetLastError();
+}
+
 static int coset_table(int log_n, uint32_t shift, PowTable* xs) {
     if (log_n < 1 || log_n > MAX_LOG_N) return (int)cudaErrorInvalidValue;
     return engine_pow_table(root_of_unity((uint32_t)log_n), log_n, shift % P, xs);

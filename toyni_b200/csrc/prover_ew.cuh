@@ -19,4 +19,6 @@ int poly_eval(const uint32_t* d_c, size_t n, uint32_t z, unsigned long long* d_a
 int merkle_gather_paths(const uint8_t* d_nodes, size_t nleaves, const unsigned long long* d_idx, size_t nq, uint32_t depth, uint8_t* d_paths,
                         cudaStream_t s);
 int gather_elems(const void* d_src, uint32_t elem_bytes, const unsigned long long* d_idx, size_t nq, void* d_out, cudaStream_t s);
+// dst[j*G + r] = src[r*chunk + j]: G runs of `chunk` elements (limbs words each) interleaved
+int interleave(const uint32_t* d_src, uint32_t* d_dst, uint32_t groups, size_t chunk, uint32_t limbs, cudaStream_t s);
 }  // namespace bb

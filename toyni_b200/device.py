@@ -120,6 +120,17 @@ def fri_fold_xs(evals, xs, beta, out=None):
     return out
 
 
+def interleave(src, groups):
+    """dst[j*G + r] = src[r*c + j] (G = groups runs of c rows each): the re-layout after the cyclic -> block exchange
+    of the sharded FRI commit."""
+    _bind_stream()
+    rows = src.shape[0]
+    limbs = 4 if src.dim() == 2 else 1
+    dst = torch.empty_like(src)
+    check(lib().bb_interleave_device(_chk(src), groups, rows // groups, limbs, _chk(dst)), "bb_interleave_device")
+    return dst
+
+
 def merkle_node_count(n):
     return lib().bb_merkle_node_count(n)
 

@@ -60,6 +60,7 @@ _SIGNATURES = {
     "bb_merkle_open_device": ([C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)], C.c_int),
     "bb_merkle_open_batch_device": ([C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)], C.c_int),
     "bb_gather_device": ([C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p], C.c_int),
+    "bb_interleave_device": ([C.c_void_p, C.c_uint32, C.c_size_t, C.c_int, C.c_void_p], C.c_int),
     "bb_fib_constraint_device": ([C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p], C.c_int),
     "bb_scale_periodic_device": ([C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32], C.c_int),
     "bb_fib_deep_device": ([C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,

@@ -12,6 +12,12 @@ Nothing like this exists in the reference (single device, default stream; SURVEY
       4. n2-point NTTs along the local rows              (bb_ntt_batch_device)
 * FRI folding: cyclic layout, rank r owns indices i = r (mod G).  The fold partner i + m/2 is on the same rank
   while m/2 >= G, so a 2^25 -> 2^4 chain needs no exchange for G <= 8 (bb_fri_fold_shard_device).
+* per-layer Merkle commits of the FRI loop (`fri_commit_sharded`): the tree pairs ADJACENT leaves
+  (src/merkle.rs:36-43), which the cyclic layout spreads over the ranks, so every layer is exchanged once from the
+  cyclic to the block layout (rank t gets leaves [t*m/G, (t+1)*m/G): one all-to-all of m/G^2 values per peer, 4 or
+  16 bytes per leaf instead of 32-byte digests), each rank hashes its leaves and builds its subtree, the G subtree
+  roots are all-gathered and the top log2(G) levels are finished redundantly on every rank's host, so that the
+  transcript (absorb root, squeeze beta) runs replicated and no broadcast is needed.
 
 The index arithmetic is written once (`fourstep_*`) and runs either on CUDA tensors with NCCL or on CPU tensors
 with gloo, which is how the N > 1 path is tested without GPUs.
@@ -251,6 +257,115 @@ def fold_chain_cuda(local, log_m, shift, betas, rank, world, until=16):
         m //= 2
         k += 1
     return layers
+
+
+# ------------------------------------------------------------------ sharded FRI commit loop
+def merkle_top(roots):
+    """Root of the tree whose leaves are the G subtree roots (node = SHA256(0x01 || L || R), src/merkle.rs:117-123)."""
+    import hashlib
+    level = [bytes(r) for r in roots]
+    while len(level) > 1:
+        level = [hashlib.sha256(b"\x01" + level[i] + level[i + 1]).digest() for i in range(0, len(level), 2)]
+    return level[0]
+
+
+def cyclic_to_block(local, world):
+    """local[j] = layer[rank + G*j]  ->  block[l] = layer[rank*m/G + l].  One all-to-all: the values of rank t's block
+    that this rank holds are the contiguous run local[t*c : (t+1)*c], c = m/G^2; on arrival the run from rank r
+    supplies block positions r, r+G, r+2G, ... (an interleave of G runs)."""
+    if world == 1:
+        return local
+    rows = local.shape[0]
+    assert rows % world == 0, "layer too small to exchange: gather it instead"
+    recv = torch.empty_like(local)
+    dist.all_to_all_single(recv, local.contiguous())
+    c = rows // world
+    if local.is_cuda:
+        from . import device as D
+        return D.interleave(recv, world)
+    tail = tuple(local.shape[1:])
+    return recv.view((world, c) + tail).transpose(0, 1).contiguous().view((rows,) + tail)
+
+
+def gather_cyclic(local, world):
+    """The whole layer in natural order on every rank (small layers at the end of the chain)."""
+    if world == 1:
+        return local
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.contiguous())
+    full = torch.stack(parts, dim=1)  # full[j][r] = layer[r + G*j]
+    return full.reshape((local.shape[0] * world,) + tuple(local.shape[1:])).contiguous()
+
+
+class CudaFriBackend:
+    """The device primitives the sharded loop is made of (C ABI kernels)."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def fold(self, local, log_m, x0, beta, world, rank):
+        from .device import fri_fold_shard
+        return fri_fold_shard(local, log_m, x0, beta, world, rank)
+
+    def commit(self, vals, salts):
+        from .device import merkle_commit
+        nodes, _ = merkle_commit(vals, salts, want_root=False)
+        return nodes, nodes[-1]  # the subtree root stays on the device: it goes straight into the all-gather
+
+    def finish(self, layer_full, x0, final_size, salts, challenge):
+        from .device import fri_commit
+        return fri_commit(layer_full, x0, final_size, salts, challenge=challenge)
+
+    def bytes_tensor(self, b):
+        return torch.frombuffer(bytearray(b), dtype=torch.uint8).to(self.device)
+
+
+def fri_commit_sharded(local0, log_m, shift, final_size, salts_for, challenge, rank, world, backend, gather_below=1 << 16):
+    """The prover's FRI commit loop (src/fibonacci.rs:200-247) over cyclic shards.
+      local0      : this rank's shard of layer 0, local0[j] = layer0[rank + G*j]  ((m/G,) or (m/G, 4))
+      salts_for   : salts_for(layer_index, lo, hi) -> (hi-lo, 16) uint8 tensor of the salts of leaves lo..hi-1 of that
+                    layer (None for the unsalted final layer), in the backend's memory
+      challenge   : challenge(root bytes, layer index) -> beta, called identically on every rank
+    Layers of at least `gather_below` values (and G^2) are committed sharded; below that the layer is all-gathered and
+    the rest of the loop runs replicated.  Returns (roots, local layers, per-layer local nodes, final layer)."""
+    m = 1 << log_m
+    x0 = shift % P
+    roots, layers, nodes = [], [local0], []
+    k = 0
+    while m > final_size and m >= gather_below and m >= world * world and (m // 2) >= world:
+        block = cyclic_to_block(layers[-1], world)
+        c = m // world
+        nd, local_root = backend.commit(block, salts_for(k, rank * c, (rank + 1) * c))
+        nodes.append(nd)
+        mine = local_root if isinstance(local_root, torch.Tensor) else backend.bytes_tensor(local_root)
+        if world > 1:
+            allr = torch.empty((world, 32), dtype=torch.uint8, device=mine.device)
+            dist.all_gather_into_tensor(allr, mine.reshape(1, 32).contiguous())
+            allr = allr.cpu().numpy()
+            root = merkle_top([allr[r].tobytes() for r in range(world)])
+        else:
+            root = mine.cpu().numpy().tobytes()
+        roots.append(root)
+        beta = challenge(root, k)
+        layers.append(backend.fold(layers[-1], log_m - k, x0, beta, world, rank))
+        x0 = x0 * x0 % P
+        m //= 2
+        k += 1
+    # tail: replicated single-device loop on the gathered layer (commits it, then folds down to final_size)
+    full = gather_cyclic(layers[-1], world)
+    off = [0]
+
+    def tail_salts():
+        parts, mm, kk = [], m, k
+        while mm > final_size:
+            parts.append(salts_for(kk, 0, mm))
+            mm //= 2
+            kk += 1
+        return torch.cat(parts).reshape(-1) if parts else None
+
+    t_layers, t_nodes, t_roots = backend.finish(full, x0, final_size, tail_salts(), lambda root, layer: challenge(root, k + layer))
+    roots.extend(t_roots)
+    return roots, layers, nodes, t_layers
 
 
 def bench_fourstep(args, rank, world, dev, log_n=27):
