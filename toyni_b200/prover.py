@@ -42,6 +42,13 @@ class FiatShamirTranscript:
         self.state = h
         return int.from_bytes(h[:8], "little") % P
 
+    def squeeze_ext_challenge(self):  # src/transcript.rs:43-50: four independent base squeezes
+        return [self.squeeze_challenge() for _ in range(4)]
+
+    def absorb_ext(self, limbs):  # src/transcript.rs:53-55: the 32 bytes of Ext::to_bytes (src/ext.rs:83-89)
+        for v in limbs:
+            self.absorb_field(v)
+
     def squeeze_indices(self, count, mx):
         out, seen = [], set()
         while len(out) < count:
