@@ -221,6 +221,7 @@ def run_ours(args, rank, world, local_rank):
     assert all(ctxs), "ntt_ctx_create failed"
 
     def pump(k, count):
+        torch.cuda.set_device(local_rank)  # the CUDA current device is per host thread
         for _ in range(count):
             L.ntt_run_inplace(ctypes.c_void_p(ctxs[k]), hosts[k].ctypes.data)
 
@@ -235,14 +236,16 @@ def run_ours(args, rank, world, local_rank):
         th.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    assert L.bb_last_error() == 0, L.bb_last_error_string()
+    e2e_err = int(L.bb_last_error())  # never raise here: the other ranks would wait in the reduction below forever
     for c in ctxs:
         L.ntt_ctx_destroy(ctypes.c_void_p(c))
-    t = torch.tensor([e2e_s, e2e_serial_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([e2e_s, e2e_serial_s, float(e2e_err)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * n * e2e_steps / float(t[0].item()) / 1e9
     e2e_serial_val = world * n * e2e_steps / float(t[1].item()) / 1e9
+    if t[2].item() != 0:
+        raise SystemExit(f"bench.py: CUDA error {int(t[2].item())} in the end-to-end path")
 
     if rank != 0:
         return
