@@ -30,12 +30,14 @@ for r in range(reps):
     p = prover.generate_proof(tr, mask, *salts)
     torch.cuda.synchronize()
     times.append(time.perf_counter() - t0)
+stages = {}
+prover.generate_proof(tr, mask, *salts, timings=stages)
 t0 = time.perf_counter()
 ok = F.verify(p, algebraic=True)
 t_verify = time.perf_counter() - t0
 out = {"trace_len": trace_len, "lde_size": lde, "fri_layers": len(p["fri_commitments"]), "prove_s": [round(t, 4) for t in times],
        "prove_best_ms": round(min(times) * 1e3, 1), "trace_generation_s": round(t_trace, 3), "verify_s": round(t_verify, 3),
-       "verifier_accepts": bool(ok)}
+       "verifier_accepts": bool(ok), "stages_ms": {k: round(v * 1e3, 2) for k, v in stages.items()}}
 print(json.dumps(out))
 json.dump(out, open(f"gpurun_out/prove_2^{log_t}.json", "w"), indent=1)
 sys.exit(0 if ok else 1)

@@ -341,6 +341,37 @@ int bb_merkle_open_device(const uint8_t* d_nodes, size_t nleaves, size_t index, 
     return note(rc);
 }
 
+// Small per-thread device scratch for the query-set entry points (indices, gathered paths / values): grow-only, so
+// that an opening costs no cudaMalloc / cudaFree (each a device-wide synchronisation) after the first call.
+namespace {
+struct SmallScratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+};
+thread_local SmallScratch g_small[2];
+int small_scratch(int slot, size_t bytes, void** out) {
+    SmallScratch& s = g_small[slot];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (s.dev != dev || s.cap < bytes) {
+        if (s.p && s.dev == dev) {
+            cudaStreamSynchronize(cur_stream());
+            cudaFree(s.p);
+        }
+        s.p = nullptr;
+        s.cap = 0;
+        size_t want = bytes < 4096 ? 4096 : bytes;
+        int rc = (int)cudaMalloc(&s.p, want);
+        if (rc) return rc;
+        s.cap = want;
+        s.dev = dev;
+    }
+    *out = s.p;
+    return 0;
+}
+}  // namespace
+
 // ---- whole query sets at once (src/fibonacci.rs:250-295): paths, and the opened values / salts
 int bb_merkle_open_batch_device(const uint8_t* d_nodes, size_t nleaves, const uint64_t* indices, size_t nq, uint8_t* paths_out,
                                 uint8_t* pos_out, size_t* depth_out) {
@@ -362,8 +393,8 @@ int bb_merkle_open_batch_device(const uint8_t* d_nodes, size_t nleaves, const ui
     cudaStream_t s = cur_stream();
     unsigned long long* d_idx = nullptr;
     uint8_t* d_paths = nullptr;
-    CK(cudaMalloc(&d_idx, nq * sizeof(unsigned long long)));
-    int rc = (int)cudaMalloc(&d_paths, nq * depth * 32);
+    CK(small_scratch(0, nq * sizeof(unsigned long long), (void**)&d_idx));
+    int rc = small_scratch(1, nq * depth * 32, (void**)&d_paths);
     if (rc == 0) rc = (int)cudaMemcpyAsync(d_idx, indices, nq * sizeof(unsigned long long), cudaMemcpyHostToDevice, s);
     if (rc == 0) rc = merkle_gather_paths(d_nodes, nleaves, d_idx, nq, (uint32_t)depth, d_paths, s);
     if (rc == 0) {
@@ -371,8 +402,6 @@ int bb_merkle_open_batch_device(const uint8_t* d_nodes, size_t nleaves, const ui
         rc = (int)cudaMemcpyAsync(paths_out, d_paths, nq * depth * 32, cudaMemcpyDeviceToHost, s);
     }
     if (rc == 0) rc = (int)cudaStreamSynchronize(s);
-    cudaFree(d_idx);
-    cudaFree(d_paths);
     return note(rc);
 }
 int bb_gather_device(const void* d_src, size_t elem_bytes, const uint64_t* indices, size_t nq, void* out) {
@@ -380,8 +409,8 @@ int bb_gather_device(const void* d_src, size_t elem_bytes, const uint64_t* indic
     cudaStream_t s = cur_stream();
     unsigned long long* d_idx = nullptr;
     uint8_t* d_out = nullptr;
-    CK(cudaMalloc(&d_idx, nq * sizeof(unsigned long long)));
-    int rc = (int)cudaMalloc(&d_out, nq * elem_bytes);
+    CK(small_scratch(0, nq * sizeof(unsigned long long), (void**)&d_idx));
+    int rc = small_scratch(1, nq * elem_bytes, (void**)&d_out);
     if (rc == 0) rc = (int)cudaMemcpyAsync(d_idx, indices, nq * sizeof(unsigned long long), cudaMemcpyHostToDevice, s);
     if (rc == 0) rc = gather_elems(d_src, (uint32_t)elem_bytes, d_idx, nq, d_out, s);
     if (rc == 0) {
@@ -389,8 +418,6 @@ int bb_gather_device(const void* d_src, size_t elem_bytes, const uint64_t* indic
         rc = (int)cudaMemcpyAsync(out, d_out, nq * elem_bytes, cudaMemcpyDeviceToHost, s);
     }
     if (rc == 0) rc = (int)cudaStreamSynchronize(s);
-    cudaFree(d_idx);
-    cudaFree(d_out);
     return note(rc);
 }
 
@@ -423,11 +450,10 @@ int bb_poly_eval_device(const uint32_t* d_coeffs, size_t n, uint32_t z, uint32_t
     cudaStream_t s = cur_stream();
     unsigned long long* d_acc = nullptr;
     unsigned long long h = 0;
-    CK(cudaMalloc(&d_acc, sizeof(unsigned long long)));
+    CK(small_scratch(0, sizeof(unsigned long long), (void**)&d_acc));
     int rc = poly_eval(d_coeffs, n, z, d_acc, s);
     if (rc == 0) rc = (int)cudaMemcpyAsync(&h, d_acc, sizeof h, cudaMemcpyDeviceToHost, s);
     if (rc == 0) rc = (int)cudaStreamSynchronize(s);
-    cudaFree(d_acc);
     g_launches++;
     if (rc == 0 && value_out) *value_out = (uint32_t)(h % (unsigned long long)P);
     return note(rc);

@@ -31,12 +31,14 @@ def _beta(beta, limbs):
 def to_device(host_u64, device="cuda"):
     """Upload a numpy uint64 field array (reference storage) as an int32 device tensor."""
     a = np.ascontiguousarray(np.asarray(host_u64, dtype=np.uint64))
-    return torch.from_numpy((a % P).astype(np.int32)).to(device)
+    if a.size and int(a.max()) >= P:  # canonical inputs (the contract, src/babybear.rs:26-30) skip the slow 64-bit modulo
+        a = a % P
+    return torch.from_numpy(a.astype(np.int32)).to(device)
 
 
 def to_host(t):
     """Download to the reference's u64 storage."""
-    return t.detach().cpu().numpy().astype(np.int64).astype(np.uint64)
+    return t.detach().cpu().numpy().astype(np.uint64)  # canonical values: the sign bit is never set
 
 
 def ntt_(t, inverse=False):

@@ -63,12 +63,14 @@ class FiatShamirTranscript:
 
 
 
-def _add(a, b):
-    return (np.asarray(a, np.uint64) + np.asarray(b, np.uint64)) % _P
+def _add(a, b):  # canonical in, canonical out: a conditional subtraction instead of numpy's slow 64-bit modulo
+    s = np.asarray(a, np.uint64) + np.asarray(b, np.uint64)
+    return s - _P * (s >= _P).astype(np.uint64)
 
 
 def _sub(a, b):
-    return (np.asarray(a, np.uint64) + _P - np.asarray(b, np.uint64)) % _P
+    s = np.asarray(a, np.uint64) + _P - np.asarray(b, np.uint64)
+    return s - _P * (s >= _P).astype(np.uint64)
 
 
 
@@ -106,9 +108,20 @@ def _as_salts(s, device):
     return torch.from_numpy(np.ascontiguousarray(s, np.uint8).reshape(-1, 16)).to(device)
 
 
-def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, device="cuda"):
+def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, device="cuda", timings=None):
     """Every array of LDE size stays on the device: LDE, constraint / quotient / DEEP formulas, commits, FRI commit
-    loop and openings.  Salts may be numpy arrays or CUDA uint8 tensors."""
+    loop and openings.  Salts may be numpy arrays or CUDA uint8 tensors.  `timings` (a dict) receives the wall time
+    of each stage in seconds, measured with a device synchronisation at every mark."""
+    import time
+    t_last = [time.perf_counter()]
+
+    def mark(name):
+        if timings is not None:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + now - t_last[0]
+            t_last[0] = now
+
     trace_len = len(trace_column)
     lde = trace_len * BLOWUP
     g = get_root_of_unity(trace_len.bit_length() - 1)
@@ -127,6 +140,7 @@ def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, devic
     trace_lde_dev = D.coset_fft(trace_poly_dev, lde, COSET_SHIFT)
     nodes, root = D.merkle_commit(trace_lde_dev, salts_trace)
     trace_tree = _Tree(trace_lde_dev, nodes, root, salts_trace)
+    mark("interpolate + LDE + trace commit")
     # 2. constraint and quotient (:133-153).  c_poly.evaluate(x) over the coset is c_evals itself (interpolate, then
     #    evaluate at the same points), and Z_H(x_i) = 7^n (w_N^n)^i - 1 takes BLOWUP values.
     c_dev = D.fib_constraint(trace_lde_dev, BLOWUP, COSET_SHIFT, pow(g, trace_len - 1, P), pow(g, trace_len - 2, P))
@@ -136,6 +150,7 @@ def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, devic
     q_coeffs_dev = D.coset_ifft_(q_dev.clone(), COSET_SHIFT)
     nodes, root = D.merkle_commit(q_dev, salts_quot)
     quot_tree = _Tree(q_dev, nodes, root, salts_quot)
+    mark("constraint + quotient + quotient commit")
     # 3. Fiat-Shamir: z outside both domains (:156-161, :378-399).  Membership without building the 2 x 32n-element
     #    sets: z is in the extended domain iff z^N = 1, in the shifted domain iff (z / 7)^N = 1, and g_ext^k z is in the
     #    shifted domain iff z is (g_ext generates the extended domain).
@@ -155,6 +170,7 @@ def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, devic
     assert c_z == q_z * ((pow(z, trace_len, P) - 1) % P) % P, "Constraint check at z failed"  # :173-177
     for v in (t_z, t_gz, t_ggz, q_z):
         tr.absorb_field(v)
+    mark("z + out-of-domain evaluations")
     # 5. DEEP polynomial (:186-198)
     d_dev = D.fib_deep(q_dev, trace_lde_dev, BLOWUP, COSET_SHIFT, z, q_z, t_z, t_gz, t_ggz)
     # 6. FRI commit loop on the device, transcript as the callback (:200-247)
@@ -166,6 +182,7 @@ def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, devic
         return tr.squeeze_challenge()
 
     layers, nodes_l, roots = D.fri_commit(d_dev, COSET_SHIFT, final_size, salts_fri.view(-1), challenge=challenge)
+    mark("DEEP + FRI commit loop")
     tr.absorb(roots[-1])  # the callback absorbed every root but the last (no fold follows it), :239-242
     trees, off = [], 0
     for k, (lay, nd) in enumerate(zip(layers, nodes_l)):
@@ -190,6 +207,8 @@ def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, devic
                     "trace_opening": trc[3 * n_q], "trace_opening_g": trc[3 * n_q + 1], "trace_opening_gg": trc[3 * n_q + 2],
                     "quotient_opening": quo[n_q],
                     "fri_openings": [(f[2 * n_q], f[2 * n_q + 1]) for f in fri]})
+    final_layer = [int(v) for v in D.to_host(layers[-1])]
+    mark("queries: openings + proof object")
     return {"trace_len": trace_len, "lde_size": lde, "trace_commitment": trace_tree.root,
             "quotient_commitment": quot_tree.root, "t_z": t_z, "t_gz": t_gz, "t_ggz": t_ggz, "q_z": q_z,
-            "fri_commitments": roots, "fri_final_layer": [int(v) for v in D.to_host(layers[-1])], "query_proofs": qps}
+            "fri_commitments": roots, "fri_final_layer": final_layer, "query_proofs": qps}
