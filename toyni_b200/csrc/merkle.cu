@@ -10,6 +10,8 @@
 
 #include "sha256.cuh"
 
+#include <mutex>
+
 namespace bb {
 
 // Leaf hash of one field value (leaf_digest in sha256.cuh).
@@ -33,7 +35,9 @@ __global__ void __launch_bounds__(256) leaf_hash_kernel(const uint32_t* __restri
 }
 
 // Parent level: node j = SHA256(0x01 || child[2j] || child[2j+1]); an odd level pairs the last child with itself.
-__device__ __forceinline__ void node_hash_one(const uint8_t* __restrict__ child, uint8_t* __restrict__ parent, size_t n_child, size_t j) {
+template <bool SMEM_TAB = false>
+__device__ __forceinline__ void node_hash_one(const uint8_t* __restrict__ child, uint8_t* __restrict__ parent, size_t n_child, size_t j,
+                                              const uint32_t* __restrict__ pad_tab) {
     size_t li = 2 * j, ri = (2 * j + 1 < n_child) ? 2 * j + 1 : 2 * j;
     const uint4* L = reinterpret_cast<const uint4*>(child + 32 * li);
     const uint4* R = reinterpret_cast<const uint4*>(child + 32 * ri);
@@ -50,31 +54,40 @@ __device__ __forceinline__ void node_hash_one(const uint8_t* __restrict__ child,
     Sha s;
     sha_init(s);
     sha_compress(s, w);
-    // second block: last message byte, 0x80, zeros, bit length 65*8
-#pragma unroll
-    for (int k = 0; k < 16; k++) w[k] = 0;
-    w[0] = (prev << 24) | 0x00800000u;
-    w[15] = 65 * 8;
-    sha_compress(s, w);
+    // second block: last message byte, 0x80, zeros, bit length 65*8 - its schedule comes from the table
+    sha_compress_tab<SMEM_TAB>(s, pad_tab, prev & 0xFFu);
     store_digest(parent + 32 * j, s);
 }
 
 __global__ void __launch_bounds__(256) node_hash_kernel(const uint8_t* __restrict__ child, uint8_t* __restrict__ parent,
-                                                        size_t n_child, size_t n_parent) {
+                                                        size_t n_child, size_t n_parent, const uint32_t* __restrict__ pad_tab) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_parent) return;
-    node_hash_one(child, parent, n_child, j);
+    node_hash_one(child, parent, n_child, j, pad_tab);
+}
+
+// Large levels: persistent CTAs keep the 64 KB padding-block table in shared memory (random 4-byte reads cost ~3 bank
+// cycles there instead of up to 8 L1 wavefronts), 512 threads each so that three CTAs still fill an SM.
+__global__ void __launch_bounds__(512) node_hash_smem_kernel(const uint8_t* __restrict__ child, uint8_t* __restrict__ parent,
+                                                             size_t n_child, size_t n_parent, const uint32_t* __restrict__ pad_tab) {
+    extern __shared__ uint32_t s_tab[];
+    for (int i = threadIdx.x; i < SHA_PAD_TAB_WORDS / 4; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_tab)[i] = __ldg(reinterpret_cast<const uint4*>(pad_tab) + i);
+    __syncthreads();
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_parent; j += (size_t)gridDim.x * blockDim.x)
+        node_hash_one<true>(child, parent, n_child, j, s_tab);
 }
 
 // Every remaining level of a small tree (n_child <= 2 * TAIL_THREADS) in ONE launch: a single CTA walks the levels
 // with a barrier between them.  The late FRI layers (and the top of every tree) are launch bound otherwise: one
 // kernel per level, 13 levels for 2^13 leaves.
 constexpr int TAIL_THREADS = 1024;
-__global__ void __launch_bounds__(TAIL_THREADS) node_hash_tail_kernel(uint8_t* __restrict__ level, size_t n_child) {
+__global__ void __launch_bounds__(TAIL_THREADS) node_hash_tail_kernel(uint8_t* __restrict__ level, size_t n_child,
+                                                                      const uint32_t* __restrict__ pad_tab) {
     while (n_child > 1) {
         uint8_t* parent = level + 32 * n_child;
         const size_t n_parent = (n_child + 1) / 2;
-        if (threadIdx.x < n_parent) node_hash_one(level, parent, n_child, threadIdx.x);
+        if (threadIdx.x < n_parent) node_hash_one(level, parent, n_child, threadIdx.x, pad_tab);
         __syncthreads();  // block-scope ordering of the global stores above with the loads of the next level
         level = parent;
         n_child = n_parent;
@@ -147,17 +160,62 @@ size_t merkle_node_count(size_t nleaves) {
     return total;
 }
 
+// K[i] + W_b[i] of the padding block of a node hash, built once per device (sha256.cuh)
+static int pad_table_get(const uint32_t** out) {
+    static std::mutex mu;
+    static uint32_t* tabs[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lk(mu);
+    uint32_t*& t = tabs[dev & 63];
+    if (!t) {
+        e = cudaMalloc(&t, SHA_PAD_TAB_WORDS * sizeof(uint32_t));
+        if (e != cudaSuccess) return (int)e;
+        sha_pad_table_kernel<<<1, 256>>>(t, 65 * 8);
+        e = cudaDeviceSynchronize();  // built on the legacy stream: visible to every stream from here on
+        if (e != cudaSuccess) {
+            cudaFree(t);
+            t = nullptr;
+            return (int)e;
+        }
+    }
+    *out = t;
+    return 0;
+}
+
 int merkle_upper_levels(uint8_t* d_nodes, size_t n, cudaStream_t s) {
+    const uint32_t* pad_tab = nullptr;
+    if (n > 1) {
+        int rc = pad_table_get(&pad_tab);
+        if (rc) return rc;
+    }
     uint8_t* cur = d_nodes;
     size_t cur_n = n;
+    static int smem_ok[64] = {};  // per device: 0 unknown, 1 configured, -1 unavailable
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    constexpr int TAB_BYTES = SHA_PAD_TAB_WORDS * 4;
     while (cur_n > (size_t)2 * TAIL_THREADS) {
         uint8_t* next = cur + 32 * cur_n;
         size_t next_n = (cur_n + 1) / 2;
-        node_hash_kernel<<<(unsigned)((next_n + 255) / 256), 256, 0, s>>>(cur, next, cur_n, next_n);
+        if (next_n >= ((size_t)1 << 18)) {
+            if (smem_ok[dev] == 0)
+                smem_ok[dev] = cudaFuncSetAttribute(node_hash_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_BYTES) == cudaSuccess ? 1 : -1;
+            if (smem_ok[dev] == 1) {
+                cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+                node_hash_smem_kernel<<<(unsigned)(3 * n_sm), 512, TAB_BYTES, s>>>(cur, next, cur_n, next_n, pad_tab);
+                cur = next;
+                cur_n = next_n;
+                continue;
+            }
+        }
+        node_hash_kernel<<<(unsigned)((next_n + 255) / 256), 256, 0, s>>>(cur, next, cur_n, next_n, pad_tab);
         cur = next;
         cur_n = next_n;
     }
-    if (cur_n > 1) node_hash_tail_kernel<<<1, TAIL_THREADS, 0, s>>>(cur, cur_n);
+    if (cur_n > 1) node_hash_tail_kernel<<<1, TAIL_THREADS, 0, s>>>(cur, cur_n, pad_tab);
     return (int)cudaGetLastError();
 }
 

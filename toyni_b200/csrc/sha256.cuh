@@ -65,6 +65,45 @@ __device__ __forceinline__ void sha_compress(Sha& s, uint32_t w[16]) {
     s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
 
+// The second block of a node hash (0x01 || L || R is 65 bytes) holds ONE message byte, 0x80, zeros and the length:
+// its whole 64-word message schedule is a function of that byte.  sha_pad_table_kernel tabulates K[i] + W_b[i] for the
+// 256 values of b (64 KB, [round][byte] so that a round reads one 1 KB row), and sha_compress_tab runs the 64 rounds
+// of that block straight from the table: no schedule arithmetic (48 x 8 ALU-pipe instructions) and no K additions.
+constexpr int SHA_PAD_TAB_WORDS = 64 * 256;
+static __global__ void sha_pad_table_kernel(uint32_t* __restrict__ tab, uint32_t bit_length) {
+    const uint32_t b = threadIdx.x;  // 256 threads
+    uint32_t w[64];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = 0;
+    w[0] = (b << 24) | 0x00800000u;
+    w[15] = bit_length;
+    for (int i = 16; i < 64; i++) {
+        const uint32_t w15 = w[i - 15], w2 = w[i - 2];
+        const uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
+        const uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    for (int i = 0; i < 64; i++) tab[i * 256 + b] = w[i] + K256[i];
+}
+
+template <bool SMEM_TAB>
+__device__ __forceinline__ void sha_compress_tab(Sha& s, const uint32_t* __restrict__ tab, uint32_t byte) {
+    uint32_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+    const uint32_t* t = tab + byte;
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        const uint32_t kw = SMEM_TAB ? t[i * 256] : __ldg(t + i * 256);
+        uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = fadd(fadd(h, S1), fadd(ch, kw));
+        uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = fadd(S0, mj);
+        h = g; g = f; f = e; e = fadd(d, t1); d = c; c = b; b = a; a = fadd(t1, t2);
+    }
+    s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+}
+
 __device__ __forceinline__ void store_digest(uint8_t* dst, const Sha& s) {
     uint4* o = reinterpret_cast<uint4*>(dst);  // 32-byte aligned
     o[0] = make_uint4(bswap(s.h[0]), bswap(s.h[1]), bswap(s.h[2]), bswap(s.h[3]));
