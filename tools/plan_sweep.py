@@ -32,6 +32,14 @@ if __name__ == "__main__":
         plans = [([12, 12], [3, 3]), ([12, 12], [2, 2]), ([8, 8, 8], [5, 5, 5]), ([8, 8, 8], [4, 4, 4]), ([8, 8, 8], [3, 3, 3]),
                  ([9, 8, 7], [5, 5, 5]), ([10, 10, 4], [3, 3, 5]), ([10, 10, 4], [4, 4, 5]), ([10, 10, 4], [5, 5, 5]), ([11, 11, 2], [3, 3, 5]),
                  ([11, 11, 2], [4, 4, 5]), ([9, 9, 6], [5, 5, 5]), ([9, 9, 6], [4, 4, 5])]
+    elif log_n == 27:
+        plans = [([9, 9, 9], [4, 4, 4]), ([9, 9, 9], [5, 5, 5]), ([9, 9, 9], [3, 3, 3]), ([10, 9, 8], [4, 4, 4]), ([8, 9, 10], [4, 4, 4]),
+                 ([10, 10, 7], [4, 4, 4]), ([7, 10, 10], [4, 4, 4]), ([11, 8, 8], [4, 4, 4]), ([8, 8, 11], [4, 4, 4]), ([8, 10, 9], [4, 4, 4]),
+                 ([10, 9, 8], [5, 5, 5]), ([9, 10, 8], [4, 4, 4])]
+    elif log_n == 26:
+        plans = [([9, 9, 8], [4, 4, 4]), ([8, 9, 9], [4, 4, 4]), ([9, 8, 9], [4, 4, 4]), ([10, 8, 8], [4, 4, 4]), ([8, 8, 10], [4, 4, 4]), ([9, 9, 8], [5, 5, 5])]
+    elif log_n == 25:
+        plans = [([9, 8, 8], [4, 4, 4]), ([8, 9, 8], [4, 4, 4]), ([8, 8, 9], [4, 4, 4]), ([9, 8, 8], [5, 5, 5])]
     elif log_n == 20:
         plans = [([10, 10], [3, 3]), ([10, 10], [4, 4]), ([10, 10], [5, 5]), ([7, 7, 6], [5, 5, 5]), ([8, 8, 4], [5, 5, 5]), ([12, 8], [3, 5])]
     elif log_n == 16:
