@@ -104,6 +104,15 @@ mod cuda {
         fn toyni_merkle_commit(values: *const u64, n: usize, limbs: i32, salts: *const u8, nodes_out: *mut u8,
                                root_out: *mut u8) -> CudaError;
         fn bb_merkle_node_count(nleaves: usize) -> usize;
+        // device-resident prover stages and query-set openings (header section 2; device pointers are *u32 / *u8)
+        fn bb_fib_constraint_device(d_trace_lde: *const u32, log_n: u32, step: u32, shift: u32, b1: u32, b2: u32, d_out: *mut u32) -> CudaError;
+        fn bb_scale_periodic_device(d_vals: *mut u32, n: usize, table: *const u32, period: u32) -> CudaError;
+        fn bb_fib_deep_device(d_quotient: *const u32, d_trace_lde: *const u32, log_n: u32, step: u32, shift: u32, z: u32,
+                              q_z: u32, t_z: u32, t_gz: u32, t_ggz: u32, d_out: *mut u32) -> CudaError;
+        fn bb_poly_eval_device(d_coeffs: *const u32, n: usize, z: u32, value_out: *mut u32) -> CudaError;
+        fn bb_merkle_open_batch_device(d_nodes: *const u8, nleaves: usize, indices: *const u64, nq: usize, paths_out: *mut u8,
+                                       pos_out: *mut u8, depth_out: *mut usize) -> CudaError;
+        fn bb_gather_device(d_src: *const c_void, elem_bytes: usize, indices: *const u64, nq: usize, out: *mut c_void) -> CudaError;
     }
 
     // BabyBear is `#[repr(C)] { value: u64 }` and Ext is `#[repr(C)] { c: [BabyBear; 4] }`
@@ -257,10 +266,58 @@ mod cuda {
         ck(unsafe { toyni_merkle_commit(evals.as_ptr() as *const u64, n, 1, sp, nodes.as_mut_ptr(), root.as_mut_ptr()) }, "CUDA Merkle commit")?;
         Ok((nodes, root))
     }
+
+    /// Device-resident column of the shifted domain (u32 per element): what `generate_proof` keeps in HBM between the
+    /// LDE and the query phase when the prover runs on the GPU (src/fibonacci.rs:124-198).
+    pub struct DeviceColumn {
+        pub ptr: *mut u32,
+        pub log_n: u32,
+    }
+    /// c_evals of src/fibonacci.rs:133-143 from the device-resident trace LDE.
+    pub fn fib_constraint_cuda(trace_lde: &DeviceColumn, out: &mut DeviceColumn, blowup: u32, shift: BabyBear, b1: BabyBear, b2: BabyBear) -> Result<(), String> {
+        ck(unsafe { bb_fib_constraint_device(trace_lde.ptr, trace_lde.log_n, blowup, shift.value as u32, b1.value as u32, b2.value as u32, out.ptr) }, "CUDA constraint evaluation")
+    }
+    /// q_evals of :147-150: multiply by the `blowup` distinct values of 1 / Z_H(x_i).
+    pub fn fib_quotient_cuda(c_evals: &mut DeviceColumn, inv_zh: &[BabyBear]) -> Result<(), String> {
+        let tab: Vec<u32> = inv_zh.iter().map(|v| v.value as u32).collect();
+        ck(unsafe { bb_scale_periodic_device(c_evals.ptr, 1usize << c_evals.log_n, tab.as_ptr(), tab.len() as u32) }, "CUDA quotient")
+    }
+    /// d_evals of :186-198.
+    pub fn fib_deep_cuda(q: &DeviceColumn, trace_lde: &DeviceColumn, out: &mut DeviceColumn, blowup: u32, shift: BabyBear, z: BabyBear,
+                         q_z: BabyBear, t_z: BabyBear, t_gz: BabyBear, t_ggz: BabyBear) -> Result<(), String> {
+        ck(unsafe { bb_fib_deep_device(q.ptr, trace_lde.ptr, trace_lde.log_n, blowup, shift.value as u32, z.value as u32, q_z.value as u32,
+                                       t_z.value as u32, t_gz.value as u32, t_ggz.value as u32, out.ptr) }, "CUDA DEEP composition")
+    }
+    /// Polynomial::evaluate (src/math/polynomial.rs:134-144) of device-resident coefficients.
+    pub fn poly_eval_cuda(d_coeffs: *const u32, n: usize, z: BabyBear) -> Result<BabyBear, String> {
+        let mut v = 0u32;
+        ck(unsafe { bb_poly_eval_device(d_coeffs, n, z.value as u32, &mut v) }, "CUDA polynomial evaluation")?;
+        Ok(BabyBear::new(v as u64))
+    }
+    /// MerkleTree::get_proof (src/merkle.rs:50-80) for a whole query set: (paths, positions), depth entries per query.
+    pub fn merkle_open_batch_cuda(d_nodes: *const u8, nleaves: usize, indices: &[u64]) -> Result<(Vec<Vec<[u8; 32]>>, Vec<Vec<bool>>), String> {
+        let mut depth = 0usize;
+        let mut m = nleaves;
+        while m > 1 { m = (m + 1) / 2; depth += 1; }
+        let mut paths = vec![0u8; indices.len() * depth * 32];
+        let mut pos = vec![0u8; indices.len() * depth];
+        ck(unsafe { bb_merkle_open_batch_device(d_nodes, nleaves, indices.as_ptr(), indices.len(), paths.as_mut_ptr(), pos.as_mut_ptr(), &mut depth) },
+           "CUDA Merkle openings")?;
+        let p = (0..indices.len()).map(|q| (0..depth).map(|d| { let mut h = [0u8; 32]; h.copy_from_slice(&paths[(q * depth + d) * 32..][..32]); h }).collect()).collect();
+        let b = (0..indices.len()).map(|q| (0..depth).map(|d| pos[q * depth + d] != 0).collect()).collect();
+        Ok((p, b))
+    }
+    /// Opened values / salts: out[q] = src[indices[q]] for elements of `elem_bytes` bytes.
+    pub fn gather_cuda(d_src: *const c_void, elem_bytes: usize, indices: &[u64]) -> Result<Vec<u8>, String> {
+        let mut out = vec![0u8; indices.len() * elem_bytes];
+        ck(unsafe { bb_gather_device(d_src, elem_bytes, indices.as_ptr(), indices.len(), out.as_mut_ptr() as *mut c_void) }, "CUDA gather")?;
+        Ok(out)
+    }
 }
 
 #[cfg(feature = "cuda")]
 pub use cuda::{
     coset_fft_cuda, coset_fft_ext_cuda, coset_ifft_cuda, coset_ifft_ext_cuda, cuda_available, fri_fold_cuda,
-    fri_fold_ext_cuda, intt_cuda, merkle_commit_cuda, ntt_cuda, CudaBuffer,
+    fib_constraint_cuda, fib_deep_cuda, fib_quotient_cuda, fri_fold_ext_cuda, gather_cuda, intt_cuda, merkle_commit_cuda,
+    merkle_open_batch_cuda, ntt_cuda, poly_eval_cuda, CudaBuffer, DeviceColumn,
 };
