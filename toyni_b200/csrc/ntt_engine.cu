@@ -266,6 +266,10 @@ static NttPlan plan_locked(int log_n, int log_inner, size_t batch) {
         pl.lr[0] = (log_n + 2) / 3;
         pl.lr[1] = (log_n - pl.lr[0] + 1) / 2;
         pl.lr[2] = log_n - pl.lr[0] - pl.lr[1];
+        // measured on B200 (tools/plan_sweep.py): the largest sizes prefer an uneven split by 1-6 %
+        if (log_n == 25) { pl.lr[0] = 8; pl.lr[1] = 8; pl.lr[2] = 9; }
+        if (log_n == 26) { pl.lr[0] = 10; pl.lr[1] = 8; pl.lr[2] = 8; }
+        if (log_n == 27) { pl.lr[0] = 8; pl.lr[1] = 10; pl.lr[2] = 9; }
     }
     for (int i = 0; i < pl.npass; i++) {
         int ncols_log = log_n - pl.lr[i] + log_inner;
@@ -414,6 +418,10 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
         p.tw = st->tw[inv];
         memcpy(p.tw16, st->tw16[inv], sizeof p.tw16);
         p.log_inner = (uint32_t)d.log_inner;
+        // Programmatic dependent launch hides the launch gap and prologue between passes (2^24: 127 -> 120 us) but was
+        // measured to slow transforms of >= 2^28 words in total by up to 27 % (64 x 2^22: 1.70 -> 2.15 ms), so it is
+        // used below that size only (tools/batch22_time.py)
+        p.pdl = (n * inner * d.batch < ((size_t)1 << 28)) ? 1u : 0u;
         p.n_in_limit = first ? (unsigned long long)d.n_in * inner : ~0ull;
 
         dim3 grid;

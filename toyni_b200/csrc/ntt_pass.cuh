@@ -61,6 +61,7 @@ struct PassParams {
     uint32_t fs_dst_row_stride;
     uint32_t fs_dst_col;
     uint32_t fs_col_offset;
+    uint32_t pdl;        // host only: launch this pass with programmatic stream serialization
     uint32_t prune_log;  // 5: blowup-32 zero padding, the first five stages of this pass are a plain copy (vector kernel)
 };
 

@@ -510,7 +510,7 @@ void launch_pass_v4(const PassParams& p, dim3 grid, cudaStream_t s) {
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (g_pdl && p.pdl) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, ntt_pass_v4_kernel<LR, LC, DB>, p, tiles_x, total);
