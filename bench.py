@@ -198,14 +198,16 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the reference-facing C ABI on pinned host buffers (every rank, max over ranks).
     # Serial: one caller, one context (what src/ntt.rs:224-236 does) - H2D, kernels, D2H strictly one after the other.
-    # Pipelined: two host threads, each with its own context and pinned buffer (ntt_ctx_create twice); one thread's
-    # H2D overlaps the other's D2H on the full-duplex PCIe link.  Both move 8 B/element each way inside the timing.
+    # Pipelined: NTHR host threads, each with its own context and pinned buffer (ntt_ctx_create once per thread); one
+    # thread's H2D overlaps another's D2H on the full-duplex PCIe link and a third's kernels.  Both forms move
+    # 8 B/element each way inside the timing.
     import ctypes
     import threading
     host = torch.empty(n, dtype=torch.int64).pin_memory()
     hv = host.numpy().view(np.uint64)
     hv[:] = (np.arange(n, dtype=np.uint64) * np.uint64(7) + np.uint64(3)) % np.uint64(2013265921)
-    e2e_steps = max(4, min(args.steps, 12)) // 2 * 2
+    NTHR = 3
+    e2e_steps = max(NTHR * 2, min(args.steps, 24)) // NTHR * NTHR
     for _ in range(2):
         host_ntt.ntt_cuda(hv)
     barrier()
@@ -215,9 +217,10 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_serial_s = time.perf_counter() - t0
 
-    hosts = [hv, torch.empty(n, dtype=torch.int64).pin_memory().numpy().view(np.uint64)]
-    hosts[1][:] = hv
-    ctxs = [L.ntt_ctx_create(n) for _ in range(2)]
+    hosts = [hv] + [torch.empty(n, dtype=torch.int64).pin_memory().numpy().view(np.uint64) for _ in range(NTHR - 1)]
+    for h in hosts[1:]:
+        h[:] = hv
+    ctxs = [L.ntt_ctx_create(n) for _ in range(NTHR)]
     assert all(ctxs), "ntt_ctx_create failed"
 
     def pump(k, count):
@@ -225,10 +228,10 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(count):
             L.ntt_run_inplace(ctypes.c_void_p(ctxs[k]), hosts[k].ctypes.data)
 
-    for k in range(2):
+    for k in range(NTHR):
         pump(k, 1)
     barrier()
-    threads = [threading.Thread(target=pump, args=(k, e2e_steps // 2)) for k in range(2)]
+    threads = [threading.Thread(target=pump, args=(k, e2e_steps // NTHR)) for k in range(NTHR)]
     t0 = time.perf_counter()
     for th in threads:
         th.start()
@@ -265,8 +268,8 @@ def run_ours(args, rank, world, local_rank):
                              "three passes move 24 B/element (a strided 64 MB-in / 64 MB-out pass alone costs 30-37 us, "
                              "tools/ubench_strided.cu) next to ~27 us of integer work per pass, see DESIGN.md and profiles/"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
-                "steps": e2e_steps, "api": "ntt_run_inplace (src/ntt.rs:108) on pinned host u64, two host threads with "
-                                           "one context each (H2D of one overlaps D2H of the other)",
+                "steps": e2e_steps, "api": f"ntt_run_inplace (src/ntt.rs:108) on pinned host u64, {NTHR} host threads with "
+                                           "one context each (H2D of one overlaps D2H and kernels of the others)",
                 "serial_value": e2e_serial_val, "serial_api": "one caller, one context: ntt_cuda as in src/ntt.rs:224-236"},
         "gpu_launches": int(launches),
         "clocks": clocks,
