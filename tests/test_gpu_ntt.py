@@ -252,6 +252,23 @@ def test_ntt_2_24_against_oracle_checksum(D):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("log_n", [17, 18, 19, 20])
+def test_large_batches_of_mid_size_vectors_use_two_long_passes(D, log_n):
+    """Batches of 2^17..2^20-point vectors with at least 2^23 words in total are planned as two passes of 256..1024 rows
+    (single vectors of the same length as three passes): both plans must give the oracle's transform."""
+    from toyni_b200.lib import lib
+    n = 1 << log_n
+    batch = (1 << 23) // n
+    x = O.random_field(batch * n, seed=300 + log_n).reshape(batch, n)
+    for inv in (False, True):
+        got = D.to_host(D.ntt_batch_(D.to_device(x), inv))
+        single = D.to_host(D.ntt_(D.to_device(x[batch - 1]), inv))
+        for r in (0, batch - 1):
+            ref = O.intt(x[r], threads=8) if inv else O.ntt(x[r], threads=8)
+            assert np.array_equal(got[r], ref)
+        assert np.array_equal(single, got[batch - 1])
+
+
 @pytest.mark.parametrize("kernel", [1, 2])
 def test_warp_private_pass_kernels_match_oracle_and_tile_kernel(D, kernel):
     """The two warp-private 256-point pass kernels (ntt_pass_v5.cuh: 8-column strips, ntt_pass_v6.cuh: 16-column

@@ -29,8 +29,14 @@ def time_batch(log_n, plan, reps=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3
 
-for log_n in (9, 10, 11, 12, 13, 14):
-    plans = [None] + [([log_n], [lc]) for lc in (2, 3, 4, 5)]
+import os
+SIZES = [int(a) for a in sys.argv[1:]] or [9, 10, 11, 12, 13, 14]
+for log_n in SIZES:
+    if log_n <= 14:
+        plans = [None] + [([log_n], [lc]) for lc in (2, 3, 4, 5)]
+    else:
+        a = (log_n + 1) // 2
+        plans = [None] + [([a, log_n - a], [lc, lc]) for lc in (3, 4, 5)] + [([log_n - a, a], [4, 4])]
     for p in plans:
         t = time_batch(log_n, p)
         print(f"log_n={log_n} plan={'default' if p is None else p}: " + (f"{t:8.1f} us {(1<<24)/t/1e3:7.1f} Gelem/s" if t else "unavailable"), flush=True)

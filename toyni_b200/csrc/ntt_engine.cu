@@ -257,10 +257,15 @@ static NttPlan plan_locked(int log_n, int log_inner, size_t batch) {
         pl.lc[0] = pick_lc(log_n, log_inner > 0 ? log_inner : 0);
         return pl;
     }
-    if (log_n <= 16) {
+    // 2^17..2^20 in two passes of 256..1024 rows when there is enough work to fill the persistent grid with such tiles
+    // (measured with tools/plan_sweep_batch.py on 2^24 words: 5-30 % faster than three passes); single short vectors
+    // keep three passes of small tiles
+    const bool two_long = log_n >= 17 && log_n <= 20 && (((size_t)batch << (log_n + log_inner)) >= ((size_t)1 << 23));
+    if (log_n <= 16 || two_long) {
         pl.npass = 2;
         pl.lr[0] = (log_n + 1) / 2;
         pl.lr[1] = log_n - pl.lr[0];
+        if (log_n == 17) { pl.lr[0] = 8; pl.lr[1] = 9; }
     } else {
         pl.npass = 3;
         pl.lr[0] = (log_n + 2) / 3;
