@@ -187,7 +187,8 @@ int bb_poly_eval_device(const uint32_t* d_coeffs, size_t n, uint32_t z, uint32_t
 /* Tuning / introspection */
 int bb_ntt_set_plan(uint32_t log_n, int npass, const int* log_rows, const int* log_cols); /* npass 0 = default */
 int bb_ntt_get_plan(uint32_t log_n, int* log_rows, int* log_cols);                        /* returns npass */
-void bb_ntt_set_kernel(int warp_private, uint32_t min_strips); /* 256-point passes: warp-private kernel (default) or tile kernel */
+void bb_ntt_set_kernel(int kernel, uint32_t min_strips); /* 256-point passes of large transforms: 0 = tile kernel (default), 1 / 2 = warp-private
+                                                            kernel with 8- / 16-column strips, used when >= min_strips strips exist (0 keeps the threshold) */
 int bb_ntt_launches(uint32_t log_n);                    /* kernels launched per device-resident transform */
 unsigned long long bb_kernel_launch_count(void);        /* total launches of this library's kernels so far */
 int bb_warmup(uint32_t log_n);                          /* build tables and scratch for this size */

@@ -540,7 +540,7 @@ int bb_ntt_get_plan(uint32_t log_n, int* log_rows, int* log_cols) {
     }
     return pl.npass;
 }
-void bb_ntt_set_kernel(int warp_private, uint32_t min_strips) { engine_enable_v5(warp_private, min_strips); }
+void bb_ntt_set_kernel(int kernel, uint32_t min_strips) { engine_enable_v5(kernel, min_strips); }
 int bb_ntt_launches(uint32_t log_n) { return ntt_plan_for((int)log_n, 0, 1).npass; }
 unsigned long long bb_kernel_launch_count(void) { return g_launches.load(); }
 int bb_warmup(uint32_t log_n) {
