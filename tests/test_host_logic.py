@@ -202,3 +202,30 @@ int main() {
     exe = tmp_path / "t.bin"
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "toyni_b200", "csrc"), str(src), "-o", str(exe)])
     assert subprocess.check_output([str(exe)]).decode().strip() == "0"
+
+
+def test_merkle_top_is_the_reference_node_hash():
+    """multigpu.merkle_top finishes a sharded tree from its subtree roots exactly like MerkleTree::build_tree
+    (src/merkle.rs:25-48): for 2^k leaves split into G blocks, root == top(roots of the blocks)."""
+    vals = O.random_field(64, seed=4)
+    salts = O.random_bytes(16 * 64, seed=5).reshape(64, 16)
+    _, root = O.commit_values(vals, salts)
+    for G in (1, 2, 4, 8):
+        c = 64 // G
+        subs = [O.commit_values(vals[r * c:(r + 1) * c], salts[r * c:(r + 1) * c])[1] for r in range(G)]
+        assert MG.merkle_top(subs) == root
+
+
+def test_pass_planner_without_a_device():
+    """The pass planner is host code behind bb_ntt_get_plan: three 256-point passes at 2^24, the measured uneven splits
+    at 2^25..2^27, two passes up to 2^16, every plan multiplying out to n."""
+    import ctypes as C
+    from toyni_b200.lib import lib
+    L = lib()
+    rows, cols = (C.c_int * 3)(), (C.c_int * 3)()
+    want = {24: [8, 8, 8], 25: [8, 8, 9], 26: [10, 8, 8], 27: [8, 10, 9], 16: [8, 8], 12: [6, 6]}
+    for log_n in range(1, 28):
+        npass = L.bb_ntt_get_plan(log_n, rows, cols)
+        assert 1 <= npass <= 3 and sum(rows[i] for i in range(npass)) == log_n
+        if log_n in want:
+            assert [rows[i] for i in range(npass)] == want[log_n]
