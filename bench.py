@@ -180,6 +180,10 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    time.sleep(0.3)  # nvidia-smi needs ~0.2 s before its first line: have it sampling when the timed region starts
+    for i in range(NB):  # back under load after the pause
+        step(i)
+    barrier()
     launches0 = L.bb_kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
