@@ -49,14 +49,18 @@ void ntt_ctx_destroy(void* ctx);                                                
  * src/ntt.rs:24-66 for the canonical root BabyBear::get_root_of_unity(log2 n). */
 void ntt_run_inplace(void* ctx, uint64_t* h_data);
 void intt_run_inplace(void* ctx, uint64_t* h_data);
+/* The same transforms with the outcome as the return value (0 or a cudaError_t): what a binding should call — the
+ * reference's void signatures cannot report a failed copy or launch (cuda/ntt_kernel.cu:249-292 ignores them). */
+int ntt_run_inplace_rc(void* ctx, uint64_t* h_data);
+int intt_run_inplace_rc(void* ctx, uint64_t* h_data);
 
 /* ------------------------------------------------------------------------------------------
  * 2. Device-resident, stream-ordered API.
  * ---------------------------------------------------------------------------------------- */
-int bb_last_error(void);                 /* sticky: first error since the last bb_clear_error() */
+int bb_last_error(void);                 /* sticky, per host thread: first error since that thread's last bb_clear_error() */
 const char* bb_last_error_string(void);
 void bb_clear_error(void);
-int bb_device_ok(void);                  /* 1 iff the current device is compute capability 10.x */
+int bb_device_ok(void);                  /* 1 iff the current device is compute capability 10.0 and the sm_100a image loads */
 /* Stream used by every later call on this host thread's library state (NULL = legacy default stream). */
 void bb_set_stream(void* cuda_stream);
 int bb_sync(void);                       /* synchronise that stream */
@@ -187,11 +191,11 @@ int bb_poly_eval_device(const uint32_t* d_coeffs, size_t n, uint32_t z, uint32_t
 /* Tuning / introspection */
 int bb_ntt_set_plan(uint32_t log_n, int npass, const int* log_rows, const int* log_cols); /* npass 0 = default */
 int bb_ntt_get_plan(uint32_t log_n, int* log_rows, int* log_cols);                        /* returns npass */
-void bb_ntt_set_kernel(int kernel, uint32_t min_strips); /* 256-point passes of large transforms: 0 = tile kernel (default), 1 / 2 = warp-private
-                                                            kernel with 8- / 16-column strips, used when >= min_strips strips exist (0 keeps the threshold) */
+void bb_ntt_set_kernel(int kernel);                     /* 1 (default): TMA-staged two-pass kernel for plain 2^24-point vectors; 0: tile kernel everywhere */
 int bb_ntt_launches(uint32_t log_n);                    /* kernels launched per device-resident transform */
 unsigned long long bb_kernel_launch_count(void);        /* total launches of this library's kernels so far */
 int bb_warmup(uint32_t log_n);                          /* build tables and scratch for this size */
+int bb_ntt_diag(uint32_t words_out[16]);                /* diagnostic words of the TMA-staged kernel: [0] time-out code (0 = none) */
 void bb_release(void);                                  /* free all cached device memory on this device */
 
 /* ------------------------------------------------------------------------------------------

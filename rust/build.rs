@@ -6,11 +6,20 @@ use std::env;
 use std::path::PathBuf;
 use std::process::Command;
 
-const SOURCES: &[&str] = &[
-    "ntt_v4_inst_a.cu", "ntt_v4_inst_b.cu", "ntt_v4_inst_c.cu", "ntt_v4_inst_d.cu", "ntt_inst_a.cu", "ntt_inst_b.cu",
-    "ntt_inst_c.cu", "ntt_inst_d.cu", "ntt_dispatch.cu", "ntt_engine.cu", "fri_fold.cu", "elementwise.cu", "merkle.cu",
-    "c_abi.cu",
-];
+// Every .cu file under cuda/ (= toyni_b200/csrc of this repository) is one translation unit of the library.  The list
+// is read from the directory, not written down twice: toyni_b200/build.py keeps an explicit list and
+// tests/test_abi_symbols.py::test_build_lists_agree checks that it names exactly the .cu files that exist.
+fn sources(dir: &PathBuf) -> Vec<String> {
+    let mut v: Vec<String> = std::fs::read_dir(dir)
+        .expect("cuda/ directory missing")
+        .filter_map(|e| e.ok())
+        .map(|e| e.file_name().to_string_lossy().into_owned())
+        .filter(|n| n.ends_with(".cu"))
+        .collect();
+    v.sort();
+    assert!(!v.is_empty(), "no .cu sources under cuda/");
+    v
+}
 
 fn main() {
     println!("cargo:rerun-if-changed=cuda");
@@ -26,7 +35,7 @@ fn main() {
     let out_dir = PathBuf::from(env::var("OUT_DIR").unwrap());
     let src_dir = PathBuf::from("cuda"); // toyni_b200/csrc + include/ of this repository copied to cuda/
     let mut objects = Vec::new();
-    for src in SOURCES {
+    for src in sources(&src_dir).iter() {
         let obj = out_dir.join(src.replace(".cu", ".o"));
         let status = Command::new(&nvcc)
             .args(["-c", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"])
@@ -50,7 +59,7 @@ fn main() {
     println!("cargo:rustc-link-search=native={cuda_home}/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    // The multi-GPU layer of this repository runs one process per GPU over torch.distributed / NCCL; a Rust host
-    // that wants the sharded paths links NCCL itself:
+    // The single-process multi-GPU entry points (bb_mg_*, header section 4) use CUDA peer access only; nothing else to
+    // link.  A host that runs one process per GPU instead links NCCL itself for its exchange:
     // println!("cargo:rustc-link-lib=dylib=nccl");
 }

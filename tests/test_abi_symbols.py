@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 import subprocess
+import tempfile
 
 from toyni_b200 import lib as L
 
@@ -35,6 +36,25 @@ def test_reference_symbols_keep_their_names():
         assert re.search(rf" T {w}$", out, flags=re.M), w
 
 
+def test_build_lists_agree():
+    """toyni_b200/build.py names its translation units explicitly; rust/build.rs compiles every .cu under cuda/ (a copy
+    of toyni_b200/csrc).  Both build the same library iff the explicit list is exactly the .cu files that exist."""
+    from toyni_b200 import build as B
+    on_disk = sorted(f for f in os.listdir(os.path.join(ROOT, "toyni_b200", "csrc")) if f.endswith(".cu"))
+    assert sorted(B.SOURCES) == on_disk
+    rs = open(os.path.join(ROOT, "rust", "build.rs")).read()
+    assert 'ends_with(".cu")' in rs and "read_dir" in rs and "arch=compute_100a,code=sm_100a" in rs
+    assert not re.search(r"sm_(7|8|9|12)\d", rs), "sm_100a only"
+
+
+def test_tma_kernel_is_in_the_library():
+    """The hot NTT pass stages its tiles with TMA: the SASS of the shipped library carries UTMALDG and mbarrier (SYNCS) ops."""
+    with tempfile.TemporaryDirectory() as td:
+        subprocess.check_call(["cuobjdump", "-xelf", "ntt_v7.sm_100a.cubin", L.library_path()], cwd=td, stdout=subprocess.DEVNULL)
+        sass = subprocess.check_output(["cuobjdump", "-sass", os.path.join(td, "ntt_v7.sm_100a.cubin")], text=True)
+    assert "ntt_pass_v7_kernel" in sass and "UTMALDG" in sass and "SYNCS" in sass
+
+
 def test_library_is_sm100a_only():
     out = subprocess.check_output(["cuobjdump", "-lelf", L.library_path()], text=True)
     archs = set(re.findall(r"sm_(\d+a?)", out))
@@ -51,7 +71,10 @@ def test_pure_host_entry_points_without_gpu():
     assert lib.bb_merkle_node_count(5) == 5 + 3 + 2 + 1
     assert lib.cuda_get_error_string(0) == b"no error"
     lr, lc = (ctypes.c_int * 3)(), (ctypes.c_int * 3)()
-    assert lib.bb_ntt_get_plan(24, lr, lc) == 3 and sum(lr) == 24
+    assert lib.bb_ntt_get_plan(24, lr, lc) == 2 and list(lr)[:2] == [12, 12]   # the TMA-staged two-pass plan
+    lib.bb_ntt_set_kernel(0)
+    assert lib.bb_ntt_get_plan(24, lr, lc) == 3 and sum(lr) == 24               # tile kernel: three passes
+    lib.bb_ntt_set_kernel(1)
     assert lib.bb_ntt_get_plan(27, lr, lc) == 3 and sum(lr) == 27
     assert lib.bb_ntt_get_plan(12, lr, lc) == 2 and sum(lr[:2]) == 12
     assert lib.ntt_ctx_create(3) is None          # not a power of two

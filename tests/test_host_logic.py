@@ -217,13 +217,13 @@ def test_merkle_top_is_the_reference_node_hash():
 
 
 def test_pass_planner_without_a_device():
-    """The pass planner is host code behind bb_ntt_get_plan: three 256-point passes at 2^24, the measured uneven splits
+    """The pass planner is host code behind bb_ntt_get_plan: two TMA-staged 4096-point passes at 2^24, the measured uneven splits
     at 2^25..2^27, two passes up to 2^16, every plan multiplying out to n."""
     import ctypes as C
     from toyni_b200.lib import lib
     L = lib()
     rows, cols = (C.c_int * 3)(), (C.c_int * 3)()
-    want = {24: [8, 8, 8], 25: [8, 8, 9], 26: [10, 8, 8], 27: [8, 10, 9], 16: [8, 8], 12: [6, 6]}
+    want = {24: [12, 12], 25: [8, 8, 9], 26: [10, 8, 8], 27: [8, 10, 9], 16: [8, 8], 12: [6, 6]}
     for log_n in range(1, 28):
         npass = L.bb_ntt_get_plan(log_n, rows, cols)
         assert 1 <= npass <= 3 and sum(rows[i] for i in range(npass)) == log_n

@@ -16,15 +16,12 @@
 using namespace bb;
 
 // ------------------------------------------------------------------ library state
-static std::atomic<int> g_last_error{0};
+static thread_local int g_last_error = 0;  // per host thread: one caller's clear cannot erase another's pending error
 static std::atomic<unsigned long long> g_launches{0};
 static thread_local cudaStream_t g_stream = nullptr;  // per host thread, as the header says
 
 static inline int note(int rc) {
-    if (rc != 0) {
-        int expected = 0;
-        g_last_error.compare_exchange_strong(expected, rc);
-    }
+    if (rc != 0 && g_last_error == 0) g_last_error = rc;  // sticky: the first error since the last bb_clear_error()
     return rc;
 }
 #define CK(x)                                  \
@@ -88,7 +85,10 @@ void* ntt_ctx_create(uint32_t n) {
         return nullptr;
     }
     uint32_t log_n = log2_of(n);
-    if (log_n > (uint32_t)MAX_LOG_N) return nullptr;  // cuda/ntt_kernel.cu:220
+    if (log_n > (uint32_t)MAX_LOG_N) {  // cuda/ntt_kernel.cu:220 returns NULL silently; here the reason is recorded
+        note((int)cudaErrorInvalidValue);
+        return nullptr;
+    }
     if (!bb_device_ok()) {
         note((int)cudaErrorNoKernelImageForDevice);
         return nullptr;
@@ -120,15 +120,12 @@ void ntt_ctx_destroy(void* ctx) {
     delete c;
 }
 
-static void run_host_inplace(NttCtx* c, uint64_t* h, bool inverse) {
-    if (!c || !h) {
-        note((int)cudaErrorInvalidValue);
-        return;
-    }
+static int run_host_inplace(NttCtx* c, uint64_t* h, bool inverse) {
+    if (!c || !h) return note((int)cudaErrorInvalidValue);
     std::lock_guard<std::mutex> lk(c->mu);
     const size_t n = c->n;
     cudaStream_t s = c->stream;
-    if (note((int)cudaMemcpyAsync(c->d64, h, n * 8, cudaMemcpyHostToDevice, s))) return;
+    CK(cudaMemcpyAsync(c->d64, h, n * 8, cudaMemcpyHostToDevice, s));
     narrow_kernel<<<conv_blocks(n), 256, 0, s>>>(c->d64, c->d32, n);
     NttDesc d{};
     d.log_n = (int)c->log_n;
@@ -138,28 +135,43 @@ static void run_host_inplace(NttCtx* c, uint64_t* h, bool inverse) {
     d.n_in = n;
     d.batch = 1;
     d.batch_stride_in = d.batch_stride_out = n;
-    if (note(ntt_execute(d, s))) return;
+    CK(ntt_execute(d, s));
     widen_kernel<<<conv_blocks(n), 256, 0, s>>>(c->d32, c->d64, n);
     g_launches += 2 + (unsigned)ntt_plan_for((int)c->log_n, 0, 1).npass;
-    if (note((int)cudaMemcpyAsync(h, c->d64, n * 8, cudaMemcpyDeviceToHost, s))) return;
-    note((int)cudaStreamSynchronize(s));
+    CK(cudaMemcpyAsync(h, c->d64, n * 8, cudaMemcpyDeviceToHost, s));
+    return note((int)cudaStreamSynchronize(s));
 }
 
 void ntt_run_inplace(void* ctx, uint64_t* h_data) { run_host_inplace((NttCtx*)ctx, h_data, false); }
 void intt_run_inplace(void* ctx, uint64_t* h_data) { run_host_inplace((NttCtx*)ctx, h_data, true); }
+// the same with the outcome as a return value (the void symbols above are what src/ntt.rs:108-109 declares)
+int ntt_run_inplace_rc(void* ctx, uint64_t* h_data) { return run_host_inplace((NttCtx*)ctx, h_data, false); }
+int intt_run_inplace_rc(void* ctx, uint64_t* h_data) { return run_host_inplace((NttCtx*)ctx, h_data, true); }
 
 // ================================================================== 2. device-resident API
-int bb_last_error(void) { return g_last_error.load(); }
-const char* bb_last_error_string(void) { return cudaGetErrorString((cudaError_t)g_last_error.load()); }
+int bb_last_error(void) { return g_last_error; }
+const char* bb_last_error_string(void) { return cudaGetErrorString((cudaError_t)g_last_error); }
 void bb_clear_error(void) {
-    g_last_error.store(0);
+    g_last_error = 0;
     cudaGetLastError();
 }
 int bb_device_ok(void) {
-    int dev = 0, major = 0;
+    // The library carries sm_100a SASS only and no PTX: arch-specific code does not run on another minor revision
+    // (e.g. sm_103), so the gate is compute capability 10.0 AND a kernel image that actually loads.
+    static std::atomic<int> cached[64];  // 0 unknown, 1 ok, 2 not ok
+    int dev = 0, major = 0, minor = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
-    return major == 10;
+    int c = cached[dev & 63].load();
+    if (c) return c == 1;
+    bool ok = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
+              cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) == cudaSuccess && major == 10 && minor == 0;
+    if (ok) {
+        cudaFuncAttributes fa;
+        ok = cudaFuncGetAttributes(&fa, narrow_kernel) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+    }
+    cached[dev & 63].store(ok ? 1 : 2);
+    return ok ? 1 : 0;
 }
 void bb_set_stream(void* cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
 int bb_sync(void) { return note((int)cudaStreamSynchronize(cur_stream())); }
@@ -217,11 +229,11 @@ struct SplitStreams {
     cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
     int dev = -1;
 };
-thread_local SplitStreams g_split;
+thread_local SplitStreams g_split[64];  // per host thread and device: nothing is dropped when the thread changes device
 int split_streams(SplitStreams** out) {
     int dev = 0;
     CK(cudaGetDevice(&dev));
-    SplitStreams& s = g_split;
+    SplitStreams& s = g_split[dev & 63];
     if (s.dev != dev) {
         for (int i = 0; i < 2; i++) {
             CK(cudaStreamCreateWithFlags(&s.h[i], cudaStreamNonBlocking));
@@ -408,13 +420,13 @@ struct SmallScratch {
     size_t cap = 0;
     int dev = -1;
 };
-thread_local SmallScratch g_small[2];
+thread_local SmallScratch g_small[64][2];  // per host thread and device
 int small_scratch(int slot, size_t bytes, void** out) {
-    SmallScratch& s = g_small[slot];
     int dev = 0;
     cudaGetDevice(&dev);
+    SmallScratch& s = g_small[dev & 63][slot];
     if (s.dev != dev || s.cap < bytes) {
-        if (s.p && s.dev == dev) {
+        if (s.p) {
             cudaStreamSynchronize(cur_stream());
             cudaFree(s.p);
         }
@@ -599,7 +611,7 @@ int bb_ntt_get_plan(uint32_t log_n, int* log_rows, int* log_cols) {
     }
     return pl.npass;
 }
-void bb_ntt_set_kernel(int kernel, uint32_t min_strips) { engine_enable_v5(kernel, min_strips); }
+void bb_ntt_set_kernel(int kernel) { engine_select_kernel(kernel); }
 int bb_ntt_launches(uint32_t log_n) { return ntt_plan_for((int)log_n, 0, 1).npass; }
 unsigned long long bb_kernel_launch_count(void) { return g_launches.load(); }
 int bb_warmup(uint32_t log_n) {
@@ -607,6 +619,7 @@ int bb_warmup(uint32_t log_n) {
     return note(engine_warmup((int)log_n, cur_stream()));
 }
 void bb_release(void) { engine_release(); }
+int bb_ntt_diag(uint32_t words_out[16]) { return note(engine_diag_words(words_out)); }
 
 }  // extern "C"
 
@@ -625,7 +638,12 @@ struct Staging {  // grow-on-demand device staging for the host-pointer entry po
     size_t nnodes = 0;
     std::mutex mu;
 };
-Staging g_stage;
+Staging g_stages[64];  // one set per device: a buffer grown on device 0 is never handed to a kernel on device 1
+Staging& cur_stage() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_stages[dev & 63];
+}
 
 template <typename T>
 int grow(T** p, size_t* have, size_t want) {
@@ -644,18 +662,18 @@ int grow(T** p, size_t* have, size_t want) {
 // upload `count` u64 values and narrow them into dst32
 int upload_narrow(const uint64_t* h, size_t count, uint32_t* dst32, cudaStream_t s) {
     if (count == 0) return 0;
-    CK(grow(&g_stage.d64, &g_stage.n64, count));
-    CK(cudaMemcpyAsync(g_stage.d64, h, count * 8, cudaMemcpyHostToDevice, s));
-    narrow_kernel<<<conv_blocks(count), 256, 0, s>>>(g_stage.d64, dst32, count);
+    CK(grow(&cur_stage().d64, &cur_stage().n64, count));
+    CK(cudaMemcpyAsync(cur_stage().d64, h, count * 8, cudaMemcpyHostToDevice, s));
+    narrow_kernel<<<conv_blocks(count), 256, 0, s>>>(cur_stage().d64, dst32, count);
     g_launches++;
     return (int)cudaGetLastError();
 }
 int widen_download(const uint32_t* src32, size_t count, uint64_t* h, cudaStream_t s) {
     if (count == 0) return 0;
-    CK(grow(&g_stage.d64, &g_stage.n64, count));
-    widen_kernel<<<conv_blocks(count), 256, 0, s>>>(src32, g_stage.d64, count);
+    CK(grow(&cur_stage().d64, &cur_stage().n64, count));
+    widen_kernel<<<conv_blocks(count), 256, 0, s>>>(src32, cur_stage().d64, count);
     g_launches++;
-    CK(cudaMemcpyAsync(h, g_stage.d64, count * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h, cur_stage().d64, count * 8, cudaMemcpyDeviceToHost, s));
     return (int)cudaStreamSynchronize(s);
 }
 
@@ -663,37 +681,37 @@ int domain_transform(const uint64_t* in, size_t n_in, size_t size, uint64_t shif
     if (!is_pow2(size) || log2_of(size) > (uint32_t)MAX_LOG_N) return note((int)cudaErrorInvalidValue);
     if (inverse && n_in != size) return note((int)cudaErrorInvalidValue);  // assert_eq!, src/math/domain.rs:86
     if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
-    std::lock_guard<std::mutex> lk(g_stage.mu);
+    std::lock_guard<std::mutex> lk(cur_stage().mu);
     cudaStream_t s = cur_stream();
     size_t take = n_in < size ? n_in : size;
-    CK(grow(&g_stage.a32, &g_stage.na, (take ? take : 1) * (size_t)limbs));
-    CK(grow(&g_stage.b32, &g_stage.nb, size * (size_t)limbs));
+    CK(grow(&cur_stage().a32, &cur_stage().na, (take ? take : 1) * (size_t)limbs));
+    CK(grow(&cur_stage().b32, &cur_stage().nb, size * (size_t)limbs));
     const uint32_t sh = (uint32_t)(shift % P);
     if (inverse) {
-        CK(upload_narrow(in, size * (size_t)limbs, g_stage.b32, s));
-        CK(bb_coset_ifft_device(g_stage.b32, log2_of(size), sh, limbs));
+        CK(upload_narrow(in, size * (size_t)limbs, cur_stage().b32, s));
+        CK(bb_coset_ifft_device(cur_stage().b32, log2_of(size), sh, limbs));
     } else {
-        CK(upload_narrow(in, take * (size_t)limbs, g_stage.a32, s));
-        CK(bb_coset_fft_device(g_stage.a32, take, log2_of(size), sh, limbs, g_stage.b32));
+        CK(upload_narrow(in, take * (size_t)limbs, cur_stage().a32, s));
+        CK(bb_coset_fft_device(cur_stage().a32, take, log2_of(size), sh, limbs, cur_stage().b32));
     }
-    return note(widen_download(g_stage.b32, size * (size_t)limbs, out, s));
+    return note(widen_download(cur_stage().b32, size * (size_t)limbs, out, s));
 }
 
 int fold_host(const uint64_t* evals, size_t m, const uint64_t* xs, const uint64_t* beta, uint64_t* out, int limbs) {
     if (m < 2 || (m & 1)) return note((int)cudaErrorInvalidValue);  // assert!, src/math/fri.rs:8,28
     if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
-    std::lock_guard<std::mutex> lk(g_stage.mu);
+    std::lock_guard<std::mutex> lk(cur_stage().mu);
     cudaStream_t s = cur_stream();
     const size_t half = m / 2;
-    CK(grow(&g_stage.a32, &g_stage.na, m * (size_t)limbs + half));
-    CK(grow(&g_stage.b32, &g_stage.nb, half * (size_t)limbs));
-    uint32_t* d_xs = g_stage.a32 + m * (size_t)limbs;
-    CK(upload_narrow(evals, m * (size_t)limbs, g_stage.a32, s));
+    CK(grow(&cur_stage().a32, &cur_stage().na, m * (size_t)limbs + half));
+    CK(grow(&cur_stage().b32, &cur_stage().nb, half * (size_t)limbs));
+    uint32_t* d_xs = cur_stage().a32 + m * (size_t)limbs;
+    CK(upload_narrow(evals, m * (size_t)limbs, cur_stage().a32, s));
     CK(upload_narrow(xs, half, d_xs, s));
     uint32_t b[4] = {0, 0, 0, 0};
     for (int k = 0; k < limbs; k++) b[k] = (uint32_t)(beta[k] % P);
-    CK(bb_fri_fold_xs_device(g_stage.a32, m, d_xs, b, limbs, g_stage.b32));
-    return note(widen_download(g_stage.b32, half * (size_t)limbs, out, s));
+    CK(bb_fri_fold_xs_device(cur_stage().a32, m, d_xs, b, limbs, cur_stage().b32));
+    return note(widen_download(cur_stage().b32, half * (size_t)limbs, out, s));
 }
 }  // namespace
 
@@ -721,20 +739,20 @@ int toyni_merkle_commit(const uint64_t* values, size_t n, int limbs, const uint8
                         uint8_t root_out[32]) {
     if (n == 0 || (limbs != 1 && limbs != 4)) return note((int)cudaErrorInvalidValue);
     if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
-    std::lock_guard<std::mutex> lk(g_stage.mu);
+    std::lock_guard<std::mutex> lk(cur_stage().mu);
     cudaStream_t s = cur_stream();
     const size_t count = merkle_node_count(n);
-    CK(grow(&g_stage.a32, &g_stage.na, n * (size_t)limbs));
-    CK(grow(&g_stage.nodes, &g_stage.nnodes, count * 32));
-    CK(upload_narrow(values, n * (size_t)limbs, g_stage.a32, s));
+    CK(grow(&cur_stage().a32, &cur_stage().na, n * (size_t)limbs));
+    CK(grow(&cur_stage().nodes, &cur_stage().nnodes, count * 32));
+    CK(upload_narrow(values, n * (size_t)limbs, cur_stage().a32, s));
     uint8_t* d_salts = nullptr;
     if (salts) {
-        CK(grow(&g_stage.bytes, &g_stage.nbytes, n * 16));
-        CK(cudaMemcpyAsync(g_stage.bytes, salts, n * 16, cudaMemcpyHostToDevice, s));
-        d_salts = g_stage.bytes;
+        CK(grow(&cur_stage().bytes, &cur_stage().nbytes, n * 16));
+        CK(cudaMemcpyAsync(cur_stage().bytes, salts, n * 16, cudaMemcpyHostToDevice, s));
+        d_salts = cur_stage().bytes;
     }
-    CK(bb_merkle_commit_device(g_stage.a32, limbs, n, d_salts, g_stage.nodes, root_out));
-    if (nodes_out) CK(cudaMemcpyAsync(nodes_out, g_stage.nodes, count * 32, cudaMemcpyDeviceToHost, s));
+    CK(bb_merkle_commit_device(cur_stage().a32, limbs, n, d_salts, cur_stage().nodes, root_out));
+    if (nodes_out) CK(cudaMemcpyAsync(nodes_out, cur_stage().nodes, count * 32, cudaMemcpyDeviceToHost, s));
     return note((int)cudaStreamSynchronize(s));
 }
 

@@ -2,7 +2,7 @@
 #include "ntt_engine.cuh"
 
 #include "fri_fold.cuh"
-#include "ntt_pass_v6.cuh"
+#include "ntt_v7.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -43,23 +43,6 @@ __global__ void gen_shoup_kernel(uint2* out, uint32_t count, uint32_t g_m) {
     }
 }
 
-// btab[e*8 + c] = Shoup pair of g^(c*e): the column-dependent factor of the first pass's inter-pass twiddle
-// (ntt_pass_v5.cuh)
-__global__ void gen_btab_kernel(uint2* out, uint32_t g_m, uint32_t log_cols) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ((uint32_t)V5_R << log_cols)) {
-        uint32_t w = from_monty(monty_pow_dev(g_m, (i >> log_cols) * (i & ((1u << log_cols) - 1u))));
-        out[i] = make_uint2(w, shoup_companion(w));
-    }
-}
-
-extern template int launch_pass_v5<V5_ROWS_CANON>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
-extern template int launch_pass_v5<V5_ROWS_TWIDDLE>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
-extern template int launch_pass_v5<V5_COLS_TWIDDLE>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
-extern template int launch_pass_v6<V5_ROWS_CANON>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
-extern template int launch_pass_v6<V5_ROWS_TWIDDLE>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
-extern template int launch_pass_v6<V5_COLS_TWIDDLE>(const PassParams&, const uint2*, uint32_t, uint32_t, cudaStream_t);
-
 // ------------------------------------------------------------------ per-device state
 struct PowTab {
     uint2* lo = nullptr;
@@ -74,7 +57,7 @@ struct DeviceState {
     // one scratch buffer per stream: transforms on different streams (e.g. two legacy contexts used from two host
     // threads) may execute concurrently and must not share the intermediate array
     std::map<cudaStream_t, std::pair<uint32_t*, size_t>> scratch;
-    std::map<std::pair<uint32_t, uint32_t>, uint2*> btabs;  // (g, log2 columns) -> table of g^(c*e), e < 256
+    uint32_t* err_word = nullptr;  // time-out diagnostics of the TMA-staged kernel
     bool ready = false;
 };
 
@@ -83,8 +66,7 @@ static std::map<int, DeviceState> g_states;
 static std::map<int, NttPlan> g_plan_override;
 static bool g_force_scalar = false;  // test hook: run every pass on the scalar kernel
 int g_pdl = 1;
-static int g_v5 = -1;                // warp-private kernel for R = 256 passes (TOYNI_NTT_V5=0 switches it off)
-static uint32_t g_v5_min_strips = 2048;
+static int g_v7 = -1;                // TMA-staged two-pass kernel for plain 2^24-point vectors (TOYNI_NTT_V7=0 switches it off)
 
 #define BB_CK(x)                          \
     do {                                  \
@@ -111,6 +93,8 @@ static int state_get(DeviceState** out) {
                 cur = bb::mul(cur, w16);
             }
         }
+        BB_CK(cudaMalloc(&st.err_word, 16 * sizeof(uint32_t)));
+        BB_CK(cudaMemset(st.err_word, 0, 16 * sizeof(uint32_t)));
         BB_CK(cudaDeviceSynchronize());
         st.ready = true;
     }
@@ -141,22 +125,6 @@ static int pow_table_get(DeviceState& st, uint32_t g, int log_total, uint32_t sc
     return 0;
 }
 
-static int btab_get(DeviceState& st, uint32_t g, uint32_t log_cols, const uint2** out) {
-    auto key = std::make_pair(g, log_cols);
-    auto it = st.btabs.find(key);
-    if (it == st.btabs.end()) {
-        uint2* t = nullptr;
-        const uint32_t cnt = (uint32_t)V5_R << log_cols;
-        BB_CK(cudaMalloc(&t, sizeof(uint2) * cnt));
-        gen_btab_kernel<<<(cnt + 255) / 256, 256>>>(t, to_monty(g), log_cols);
-        BB_CK(cudaGetLastError());
-        BB_CK(cudaDeviceSynchronize());
-        it = st.btabs.emplace(key, t).first;
-    }
-    *out = it->second;
-    return 0;
-}
-
 static int scratch_get(DeviceState& st, cudaStream_t stream, size_t words, uint32_t** out) {
     auto& slot = st.scratch[stream];
     if (slot.second < words) {
@@ -179,6 +147,14 @@ int engine_pow_table(uint32_t g, int log_total, uint32_t scale, PowTable* out) {
     int rc = state_get(&st);
     if (rc) return rc;
     return pow_table_get(*st, g, log_total, scale, out);
+}
+
+int engine_diag_words(uint32_t out[16]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState* st;
+    int rc = state_get(&st);
+    if (rc) return rc;
+    return (int)cudaMemcpy(out, st->err_word, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
 }
 
 size_t engine_scratch_bytes() {
@@ -206,7 +182,7 @@ void engine_release() {
         cudaFree(kv.second.hi);
     }
     for (auto& kv : st.scratch) cudaFree(kv.second.first);
-    for (auto& kv : st.btabs) cudaFree(kv.second);
+    cudaFree(st.err_word);
     g_states.erase(it);
 }
 
@@ -234,11 +210,28 @@ void ntt_plan_override(int log_n, const NttPlan& plan) {
         g_plan_override[log_n] = plan;
 }
 
-static NttPlan plan_locked(int log_n, int log_inner, size_t batch) {
+static bool v7_enabled() {
+    if (g_v7 < 0) {
+        const char* e = getenv("TOYNI_NTT_V7");
+        g_v7 = e ? atoi(e) : 1;
+        const char* e2 = getenv("TOYNI_NTT_PDL");
+        if (e2) g_pdl = atoi(e2);
+    }
+    return g_v7 != 0 && !g_force_scalar;
+}
+
+static NttPlan plan_locked(int log_n, int log_inner, size_t batch, bool allow_v7 = true) {
     auto it = g_plan_override.find(log_n);
     if (it != g_plan_override.end()) return it->second;
     NttPlan pl;
     memset(&pl, 0, sizeof pl);
+    if (allow_v7 && log_n == 2 * V7_LR && log_inner == 0 && v7_enabled()) {
+        // 4096 x 4096 in two TMA-staged passes (ntt_pass_v7.cuh): 16 instead of 24 bytes of traffic per element
+        pl.npass = 2;
+        pl.lr[0] = pl.lr[1] = V7_LR;
+        pl.lc[0] = pl.lc[1] = 3;
+        return pl;
+    }
     // Measured on B200 (tools/plan_sweep.py): passes of about 2^8 rows x 16 columns (16 KB tiles, double buffered,
     // 7 CTAs per SM) beat fewer, larger passes — the kernels are instruction-bound, not DRAM-bound, and the
     // intermediate arrays of a <= 2^24 transform mostly stay in the 126 MB L2.
@@ -285,10 +278,58 @@ static NttPlan plan_locked(int log_n, int log_inner, size_t batch) {
     return pl;
 }
 
-void engine_enable_v5(int on, uint32_t min_strips) {
+void engine_select_kernel(int kernel) {
     std::lock_guard<std::mutex> lk(g_mu);
-    g_v5 = on;  // 0 tile kernel, 1 warp-private 8-column strips, 2 warp-private 16-column strips
-    if (min_strips) g_v5_min_strips = min_strips;
+    g_v7 = kernel != 0;  // 0: tile kernel everywhere; otherwise the TMA-staged kernel where it applies (default)
+}
+
+// plain 2^24-point vectors: two passes of the TMA-staged kernel.  Tables and scratch are looked up under the engine
+// lock (v7_prepare); the launches themselves run without it.
+struct V7Job {
+    V7Params p;
+    uint32_t* scratch;
+    bool pdl;
+};
+
+static int v7_prepare(DeviceState& st, const NttDesc& d, cudaStream_t stream, V7Job* job) {
+    const int inv = d.inverse ? 1 : 0;
+    const size_t n = (size_t)1 << d.log_n;
+    uint32_t omega = root_of_unity(d.log_n);
+    if (inv) omega = bb::inv(omega);
+    V7Params& p = job->p;
+    memset(&p, 0, sizeof p);
+    int rc = pow_table_get(st, omega, d.log_n, 1u, &p.tab);
+    if (rc) return rc;
+    p.tab_scaled = p.tab;
+    if (inv) {
+        rc = pow_table_get(st, omega, d.log_n, bb::inv((uint32_t)(n % P)), &p.tab_scaled);
+        if (rc) return rc;
+    }
+    rc = scratch_get(st, stream, n * d.batch, &job->scratch);
+    if (rc) return rc;
+    p.tw = st.tw[inv];
+    memcpy(p.tw16, st.tw16[inv], sizeof p.tw16);
+    p.exp_mask = (uint32_t)(n - 1);
+    p.err = st.err_word;
+    job->pdl = n * d.batch < ((size_t)1 << 28);
+    return 0;
+}
+
+static int v7_launch(const NttDesc& d, V7Job& job, cudaStream_t stream) {
+    const size_t n = (size_t)1 << d.log_n;
+    const size_t ncols = n >> V7_LR;
+    V7Params p = job.p;
+    // pass 1: columns of in[4096][ncols] -> scratch[col][e]
+    p.out = job.scratch;
+    p.out_batch_stride = n;
+    p.log_pfull = 0;
+    int rc = launch_pass_v7(false, d.in, ncols, d.batch, d.batch_stride_in, p, job.pdl, stream);
+    if (rc) return rc;
+    // pass 2: columns of scratch[ncols][4096] (rows = columns of pass 1) -> out[e2 * 4096 + e1]
+    p.out = d.out;
+    p.out_batch_stride = d.batch_stride_out;
+    p.log_pfull = V7_LR;
+    return launch_pass_v7(true, job.scratch, (size_t)V7_R, d.batch, n, p, job.pdl, stream);
 }
 
 NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch) {
@@ -337,7 +378,9 @@ int engine_warmup(int log_n, cudaStream_t stream) {
 int ntt_execute(const NttDesc& d, cudaStream_t stream) {
     if (d.log_n < 0 || d.log_n > MAX_LOG_N) return (int)cudaErrorInvalidValue;
     if (d.batch == 0) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);
+    // the lock covers planning, table and scratch look-ups; the kernel launches below run without it, so transforms
+    // issued from several host threads (or for several devices) do not serialise on the host
+    std::unique_lock<std::mutex> lk(g_mu);
     DeviceState* st;
     int rc = state_get(&st);
     if (rc) return rc;
@@ -346,7 +389,16 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
     const size_t n = (size_t)1 << d.log_n;
     const size_t inner = (size_t)1 << d.log_inner;
     const bool coset = d.coset_shift > 1;
-    const NttPlan pl = plan_locked(d.log_n, d.log_inner, d.batch);
+    const bool use_v7 = d.log_n == 2 * V7_LR && d.log_inner == 0 && !coset && !d.scatter && d.n_in == n && v7_enabled() &&
+                        g_plan_override.find(d.log_n) == g_plan_override.end() && ((((uintptr_t)d.in | (uintptr_t)d.out) & 15u) == 0) &&
+                        (d.batch == 1 || (d.batch_stride_in % 4 == 0 && d.batch_stride_out % 4 == 0));
+    if (use_v7) {
+        V7Job job;
+        rc = v7_prepare(*st, d, stream, &job);
+        lk.unlock();
+        return rc ? rc : v7_launch(d, job, stream);
+    }
+    const NttPlan pl = plan_locked(d.log_n, d.log_inner, d.batch, false);
 
     const uint32_t n_inv = bb::inv((uint32_t)(n % P));
     uint32_t omega = root_of_unity(d.log_n);
@@ -390,6 +442,12 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
     const bool transposed = (pl.npass == 1 && d.log_inner == 0);
     if (transposed && d.batch > 1 && (d.batch_stride_out != n)) return (int)cudaErrorInvalidValue;
 
+    const uint2* tw_dir = st->tw[inv];
+    uint2 tw16_dir[8];
+    memcpy(tw16_dir, st->tw16[inv], sizeof tw16_dir);
+    const bool force_scalar = g_force_scalar;
+    lk.unlock();
+
     int log_p = 0;  // log2(R_1 ... R_{i-1})
     for (int i = 0; i < pl.npass; i++) {
         const int lr = pl.lr[i], lc = pl.lc[i];
@@ -420,8 +478,8 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
         }
         p.in = src;
         p.out = dst;
-        p.tw = st->tw[inv];
-        memcpy(p.tw16, st->tw16[inv], sizeof p.tw16);
+        p.tw = tw_dir;
+        memcpy(p.tw16, tw16_dir, sizeof p.tw16);
         p.log_inner = (uint32_t)d.log_inner;
         // Programmatic dependent launch hides the launch gap and prologue between passes (2^24: 127 -> 120 us) but was
         // measured to slow transforms of >= 2^28 words in total by up to 27 % (64 x 2^22: 1.70 -> 2.15 ms), so it is
@@ -479,50 +537,9 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
             p.epi_mode = EPI_NONE;
         }
         const bool aligned = ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) && (src_bs % 4 == 0) && (dst_bs % 4 == 0);
-        // warp-private kernel: full-length 256-point passes of large transforms (plain twiddle or no epilogue)
-        if (g_v5 < 0) {
-            const char* e = getenv("TOYNI_NTT_V5");
-            g_v5 = e ? atoi(e) : 0;
-            const char* e2 = getenv("TOYNI_NTT_PDL");
-            if (e2) g_pdl = atoi(e2);
-        }
-        if (g_v5 && !g_force_scalar && !transposed && lr == V5_LR && aligned && p.pro_mode == PRO_NONE &&
-            (!first || d.n_in == n) && (p.ncols % 32u) == 0 &&
-            (size_t)(p.ncols / 8u) * d.batch >= g_v5_min_strips && (size_t)(p.ncols / 8u) * d.batch < (1ull << 31) &&
-            ((p.epi_mode == EPI_NONE && p.log_pfull >= 4) ||
-             (p.epi_mode == EPI_TWIDDLE && (p.log_pfull >= 4 || (p.log_pfull == 0 && d.log_inner == 0))))) {
-            if (g_v5 == 2) {  // wide strips (16 columns)
-                const uint32_t strips_x = p.ncols / 16u;
-                if (p.epi_mode == EPI_NONE) {
-                    rc = launch_pass_v6<V5_ROWS_CANON>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
-                } else if (p.log_pfull >= 4) {
-                    rc = launch_pass_v6<V5_ROWS_TWIDDLE>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
-                } else {
-                    const uint2* btab = nullptr;
-                    rc = btab_get(*st, bb::pow(omega, 1ull << p.epi_shift), 4, &btab);
-                    if (rc) return rc;
-                    rc = launch_pass_v6<V5_COLS_TWIDDLE>(p, btab, strips_x, (uint32_t)d.batch, stream);
-                }
-            } else {
-                const uint32_t strips_x = p.ncols / 8u;
-                if (p.epi_mode == EPI_NONE) {
-                    rc = launch_pass_v5<V5_ROWS_CANON>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
-                } else if (p.log_pfull >= 3) {
-                    rc = launch_pass_v5<V5_ROWS_TWIDDLE>(p, nullptr, strips_x, (uint32_t)d.batch, stream);
-                } else {
-                    const uint2* btab = nullptr;
-                    rc = btab_get(*st, bb::pow(omega, 1ull << p.epi_shift), 3, &btab);
-                    if (rc) return rc;
-                    rc = launch_pass_v5<V5_COLS_TWIDDLE>(p, btab, strips_x, (uint32_t)d.batch, stream);
-                }
-            }
-            if (rc) return rc;
-            log_p += lr;
-            continue;
-        }
         // vectorised kernel whenever chunks of four columns stay whole; scalar kernel otherwise
         PassLaunchFn fn = nullptr;
-        if (!transposed && lc >= 2 && aligned && p.log_pfull != 1 && (p.ncols & ((1u << lc) - 1u)) == 0 && !g_force_scalar)
+        if (!transposed && lc >= 2 && aligned && p.log_pfull != 1 && (p.ncols & ((1u << lc) - 1u)) == 0 && !force_scalar)
             fn = pass_launcher_v4(lr, lc);
         if (fn && first && !inv && lr >= 6 && lr <= 9 && d.n_in * 32 == n && p.in_batch_stride % 4 == 0) {
             // exactly the first R/32 rows of every tile hold input (blowup 32): prune the copy-only stages

@@ -49,12 +49,12 @@ NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch);
 void ntt_plan_override(int log_n, const NttPlan& plan);
 PassLaunchFn pass_launcher(int lr, int lc);     // scalar kernel; nullptr if that tile shape is not built
 PassLaunchFn pass_launcher_v4(int lr, int lc);  // vectorised kernel (LC >= 2)
-// R = 256 passes of large transforms run on the warp-private kernel (ntt_pass_v5.cuh) when at least `min_strips`
-// strips of 8 columns exist (0 keeps the current threshold); on = 0 sends them to the tile kernel instead
-void engine_enable_v5(int on, uint32_t min_strips);
+// 0: tile kernel (ntt_pass_v4.cuh) for every size; 1 (default): TMA-staged two-pass kernel (ntt_pass_v7.cuh) where it applies
+void engine_select_kernel(int kernel);
 int engine_warmup(int log_n, cudaStream_t stream);  // build tables / this stream's scratch ahead of time
 void engine_drop_stream(cudaStream_t stream);       // free the scratch kept for a stream that is going away
 size_t engine_scratch_bytes();
+int engine_diag_words(uint32_t out[16]);           // time-out / diagnostic words of the TMA-staged kernel (synchronises)
 void engine_release();                       // free every cached device allocation on the current device
 
 }  // namespace bb

@@ -167,6 +167,13 @@ BB_D uint32_t pow_lookup(const PowTable& t, uint32_t e) {
     const uint32_t w = shoup_mul_lazy(lo.x, hi.x, hi.y);  // lo*hi in [0,2p)
     return monty_mul(w, R2_MOD_P);                         // canonical, times R
 }
+// canonical g^e (times the table's constant factor), plain form
+BB_D uint32_t pow_plain(const PowTable& t, uint32_t e) {
+    const uint2 lo = __ldg(&t.lo[e & ((1u << t.lo_bits) - 1u)]);
+    const uint2 hi = __ldg(&t.hi[e >> t.lo_bits]);
+    const uint32_t w = shoup_mul_lazy(lo.x, hi.x, hi.y);
+    return min(w, w - P);
+}
 // v * g^e, canonical, for any 32-bit v: two Shoup multiplications, no product twiddle formed
 BB_D uint32_t pow_apply(const PowTable& t, uint32_t e, uint32_t v) {
     const uint2 lo = __ldg(&t.lo[e & ((1u << t.lo_bits) - 1u)]);

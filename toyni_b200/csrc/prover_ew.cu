@@ -14,7 +14,7 @@
 #include "fri_fold.cuh"
 #include "merkle.cuh"
 #include "ntt_engine.cuh"
-#include "ntt_pass_v5.cuh"
+#include "ntt_pass_v4.cuh"
 #include "prover_ew.cuh"
 
 namespace bb {

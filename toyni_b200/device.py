@@ -241,13 +241,28 @@ def fri_commit(layer0, shift, final_size, salts=None, challenge=None, betas=None
     if hash_layers:
         nodes = torch.empty((sum(merkle_node_count(s) for s in sizes), 32), dtype=torch.uint8, device=dev)
         roots = np.zeros((len(sizes), 32), dtype=np.uint8)
+    if salts is not None and hash_layers:
+        # 16 bytes per leaf of every salted (= non-final) layer, back to back: the fused fold + leaf-hash kernels read
+        # straight through this pointer
+        need = 16 * sum(sizes[:-1])
+        assert salts.is_cuda and salts.dtype == torch.uint8 and salts.is_contiguous(), "salts: contiguous uint8 CUDA tensor"
+        assert salts.numel() >= need, f"salts: {salts.numel()} bytes given, {need} needed for layers {sizes[:-1]}"
     cb = None
+    cb_error = []
     if challenge is not None:
         def _cb(_user, root_ptr, layer, beta_out):
-            b = challenge(bytes(root_ptr[:32]), int(layer))
-            vals = [int(b)] if limbs == 1 else [int(x) for x in b]
-            for k, v in enumerate(vals):
-                beta_out[k] = v % P
+            # ctypes swallows exceptions raised inside a callback: keep the first one and re-raise it after the C call
+            # (beta stays 0 for the remaining layers; their results are discarded)
+            if cb_error:
+                return
+            try:
+                b = challenge(bytes(root_ptr[:32]), int(layer))
+                vals = [int(b)] if limbs == 1 else [int(x) for x in b]
+                assert len(vals) == limbs, f"challenge returned {len(vals)} limbs, {limbs} expected"
+                for k, v in enumerate(vals):
+                    beta_out[k] = v % P
+            except BaseException as e:  # noqa: BLE001 - re-raised below
+                cb_error.append(e)
         cb = CHALLENGE_FN(_cb)
     bt = None
     if betas is not None:
@@ -259,6 +274,8 @@ def fri_commit(layer0, shift, final_size, salts=None, challenge=None, betas=None
                                      None if bt is None else bt.ctypes.data, _chk(layers),
                                      None if nodes is None else C.c_void_p(nodes.data_ptr()),
                                      None if roots is None else roots.ctypes.data, C.byref(folds)), "bb_fri_commit_device")
+    if cb_error:
+        raise cb_error[0]
     out_layers, out_nodes, off, noff = [], [], 0, 0
     for k, s in enumerate(sizes):
         if k == 0:

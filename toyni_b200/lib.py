@@ -23,6 +23,8 @@ _SIGNATURES = {
     "ntt_ctx_destroy": ([C.c_void_p], None),
     "ntt_run_inplace": ([C.c_void_p, C.c_void_p], None),
     "intt_run_inplace": ([C.c_void_p, C.c_void_p], None),
+    "ntt_run_inplace_rc": ([C.c_void_p, C.c_void_p], C.c_int),
+    "intt_run_inplace_rc": ([C.c_void_p, C.c_void_p], C.c_int),
     # 2. device-resident API
     "bb_last_error": ([], C.c_int),
     "bb_last_error_string": ([], C.c_char_p),
@@ -70,7 +72,8 @@ _SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)], C.c_int),
     "bb_ntt_set_plan": ([C.c_uint32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     "bb_ntt_get_plan": ([C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
-    "bb_ntt_set_kernel": ([C.c_int, C.c_uint32], None),
+    "bb_ntt_set_kernel": ([C.c_int], None),
+    "bb_ntt_diag": ([C.POINTER(C.c_uint32)], C.c_int),
     "bb_ntt_launches": ([C.c_uint32], C.c_int),
     "bb_kernel_launch_count": ([], C.c_ulonglong),
     "bb_warmup": ([C.c_uint32], C.c_int),

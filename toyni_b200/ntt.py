@@ -74,9 +74,8 @@ def _run(values, inverse):
     assert n.bit_length() - 1 <= 27, "BabyBear only supports NTT up to 2^27"  # :230
     ctx = _get_or_create_ctx(n)
     L = lib()
-    L.bb_clear_error()
-    (L.intt_run_inplace if inverse else L.ntt_run_inplace)(ctx, values.ctypes.data)
-    err = L.bb_last_error()  # the reference's void entry points swallow errors; this library keeps them
+    # the reference's void entry points (src/ntt.rs:108-109) cannot report a failed copy or launch; the _rc forms can
+    err = (L.intt_run_inplace_rc if inverse else L.ntt_run_inplace_rc)(ctx, values.ctypes.data)
     if err:
         raise ToyniCudaError("CUDA NTT failed: " + L.cuda_get_error_string(err).decode())
 

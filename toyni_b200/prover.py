@@ -124,6 +124,9 @@ def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, devic
 
     trace_len = len(trace_column)
     lde = trace_len * BLOWUP
+    mask = np.asarray(mask, dtype=np.uint64).reshape(-1)
+    # the reference draws exactly MASK_DEGREE blinding coefficients (src/fibonacci.rs:117-120); a scalar would broadcast
+    assert mask.size == MASK_DEGREE, f"mask: {mask.size} coefficients given, {MASK_DEGREE} required"
     g = get_root_of_unity(trace_len.bit_length() - 1)
     salts_trace, salts_quot = _as_salts(salts_trace, device), _as_salts(salts_quot, device)
     salts_fri = _as_salts(salts_fri, device)
