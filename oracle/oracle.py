@@ -70,6 +70,7 @@ def lib():
             "to_transcript_squeeze_indices": ([C.POINTER(Transcript), sz, sz, u64p], None),
             "to_fri_commit": ([u64p, sz, u64, sz, u8p, C.POINTER(Transcript), u64p, u8p, u64p], sz),
             "to_fri_commit_ext": ([u64p, sz, u64, sz, u8p, C.POINTER(Transcript), u64p, u8p, u64p], sz),
+            "to_set_threads": ([C.c_int], None), "to_get_threads": ([], C.c_int),
             "to_fill_random": ([u64p, sz, u64], None), "to_fill_random_bytes": ([u8p, sz, u64], None),
         }
         for name, (args, res) in sig.items():
@@ -94,6 +95,12 @@ def _p8(a):
 
 def _arr(x):
     return np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+
+
+def set_threads(threads):
+    """Thread count of the element-wise oracle loops (coset shift, folds, hashing) and of the transforms inside
+    domain_fft / domain_ifft; 1 = the reference's serial loops verbatim.  Same bits either way."""
+    lib().to_set_threads(int(threads))
 
 
 # ---- field -------------------------------------------------------------------------------

@@ -139,6 +139,35 @@ void to_ntt(uint64_t* v, size_t n, uint64_t omega) { /* src/ntt.rs:24-53 */
     }
 }
 
+/* Thread count for the element-wise loops below (coset shift, folds, leaf / node hashing) and for the transforms inside
+ * to_domain_fft / to_domain_ifft.  1 (the default) runs the reference's serial loops verbatim; > 1 cuts the same loops
+ * into chunks over OpenMP — identical arithmetic per element (a chunk restarts a running power at shift^i0, exactly the
+ * value the serial loop reaches there), so the results are the same bits.  Used for full-size parity checks. */
+static int g_threads = 1;
+void to_set_threads(int threads) { g_threads = threads > 1 ? threads : 1; }
+int to_get_threads(void) { return g_threads; }
+
+static void scale_by_powers(uint64_t* v, size_t n, uint64_t g) { /* v[i] *= g^i, the loops of src/math/domain.rs:154-174 */
+    if (g_threads <= 1 || n < 8192) {
+        uint64_t sp = 1;
+        for (size_t i = 0; i < n; i++) {
+            v[i] = to_bb_mul(v[i], sp);
+            sp = to_bb_mul(sp, g);
+        }
+        return;
+    }
+    const size_t chunk = 4096, nchunks = (n + chunk - 1) / chunk;
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (size_t c = 0; c < nchunks; c++) {
+        size_t i0 = c * chunk, i1 = i0 + chunk < n ? i0 + chunk : n;
+        uint64_t sp = to_bb_pow(g, (uint64_t)i0);
+        for (size_t i = i0; i < i1; i++) {
+            v[i] = to_bb_mul(v[i], sp);
+            sp = to_bb_mul(sp, g);
+        }
+    }
+}
+
 void to_intt(uint64_t* v, size_t n, uint64_t omega) { /* src/ntt.rs:56-66 */
     uint64_t inv_omega = to_bb_pow(omega, (uint64_t)n - 1);
     to_ntt(v, n, inv_omega);
@@ -219,28 +248,18 @@ void to_domain_fft(const uint64_t* coeffs, size_t ncoeffs, size_t size, uint64_t
     size_t take = ncoeffs < size ? ncoeffs : size;
     memcpy(out, coeffs, take * sizeof(uint64_t));
     memset(out + take, 0, (size - take) * sizeof(uint64_t));
-    if (shift != 1) { /* apply_coset_shift, :154-162 */
-        uint64_t sp = 1;
-        for (size_t i = 0; i < size; i++) {
-            out[i] = to_bb_mul(out[i], sp);
-            sp = to_bb_mul(sp, shift);
-        }
-    }
-    to_ntt(out, size, to_bb_root_of_unity(log2_exact(size)));
+    if (shift != 1) scale_by_powers(out, size, shift); /* apply_coset_shift, :154-162 */
+    to_ntt_mt(out, size, to_bb_root_of_unity(log2_exact(size)), g_threads);
 }
 
 void to_domain_ifft(const uint64_t* evals, size_t size, uint64_t shift, uint64_t* out) {
     /* src/math/domain.rs:85-102 */
     memcpy(out, evals, size * sizeof(uint64_t));
-    to_intt(out, size, to_bb_root_of_unity(log2_exact(size)));
-    if (shift != 1) { /* undo_coset_shift, :165-174 */
-        uint64_t shift_inv = to_bb_inverse(shift);
-        uint64_t sp = 1;
-        for (size_t i = 0; i < size; i++) {
-            out[i] = to_bb_mul(out[i], sp);
-            sp = to_bb_mul(sp, shift_inv);
-        }
-    }
+    if (g_threads > 1)
+        to_intt_mt(out, size, to_bb_root_of_unity(log2_exact(size)), g_threads);
+    else
+        to_intt(out, size, to_bb_root_of_unity(log2_exact(size)));
+    if (shift != 1) scale_by_powers(out, size, to_bb_inverse(shift)); /* undo_coset_shift, :165-174 */
 }
 
 static void transform_ext(const uint64_t* in, size_t nin, size_t size, uint64_t shift, uint64_t* out, int inverse) {
@@ -273,6 +292,7 @@ void to_fri_fold(const uint64_t* evals, size_t m, const uint64_t* xs, uint64_t b
     /* src/math/fri.rs:27-48 */
     size_t half = m / 2;
     uint64_t half_inv = to_bb_inverse(to_bb_new(2));
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && half >= 4096)
     for (size_t i = 0; i < half; i++) {
         uint64_t a = evals[i], b = evals[i + half], x = xs[i];
         uint64_t avg = to_bb_mul(to_bb_add(a, b), half_inv);
@@ -285,6 +305,7 @@ void to_fri_fold_ext(const uint64_t* evals, size_t m, const uint64_t* xs, const 
     /* src/math/fri.rs:7-25 */
     size_t half = m / 2;
     uint64_t half_inv = to_bb_inverse(to_bb_new(2));
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && half >= 4096)
     for (size_t i = 0; i < half; i++) {
         const uint64_t* a = evals + 4 * i;
         const uint64_t* b = evals + 4 * (i + half);
@@ -426,6 +447,7 @@ static void merkle_upper_levels(uint8_t* nodes, size_t nleaves, uint8_t root_out
     while (cur_n > 1) {
         uint8_t* next = cur + 32 * cur_n;
         size_t next_n = (cur_n + 1) / 2;
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && cur_n >= 4096)
         for (size_t i = 0; i < cur_n; i += 2) {
             const uint8_t* l = cur + 32 * i;
             const uint8_t* r = (i + 1 < cur_n) ? cur + 32 * (i + 1) : l;
@@ -438,6 +460,7 @@ static void merkle_upper_levels(uint8_t* nodes, size_t nleaves, uint8_t root_out
 }
 
 void to_merkle_build(const uint8_t* leaves, size_t nleaves, size_t leaf_len, uint8_t* nodes_out, uint8_t root_out[32]) {
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && nleaves >= 4096)
     for (size_t i = 0; i < nleaves; i++) to_hash_leaf(leaves + i * leaf_len, leaf_len, nodes_out + 32 * i); /* :29-31 */
     merkle_upper_levels(nodes_out, nleaves, root_out);
 }
@@ -445,9 +468,10 @@ void to_merkle_build(const uint8_t* leaves, size_t nleaves, size_t leaf_len, uin
 void to_commit_values(const uint64_t* values, size_t n, int limbs, const uint8_t* salts, uint8_t* nodes_out,
                       uint8_t root_out[32]) {
     /* src/fibonacci.rs:340-363: leaf = salt || value.to_bytes(), or just value.to_bytes() */
-    uint8_t leaf[16 + 32];
     size_t vbytes = 8 * (size_t)limbs;
+#pragma omp parallel for num_threads(g_threads) schedule(static) if (g_threads > 1 && n >= 4096)
     for (size_t i = 0; i < n; i++) {
+        uint8_t leaf[16 + 32];
         size_t off = 0;
         if (salts) {
             memcpy(leaf, salts + 16 * i, 16);

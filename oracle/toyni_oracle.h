@@ -62,6 +62,10 @@ void to_intt_mt(uint64_t* values, size_t n, uint64_t omega, int threads);
 /* ---- Evaluation domain (src/math/domain.rs) ---- */
 void to_domain_elements(uint64_t* out, size_t size, uint64_t shift);                          /* :61-69 */
 /* fft: zero-pad / truncate coeffs to `size`, coset shift, forward NTT (:107-123,154-162) */
+/* thread count of the element-wise loops and of the transforms inside to_domain_fft / ifft (1 = the reference's serial
+ * loops verbatim; more = the same arithmetic cut into chunks, same bits) */
+void to_set_threads(int threads);
+int to_get_threads(void);
 void to_domain_fft(const uint64_t* coeffs, size_t ncoeffs, size_t size, uint64_t shift, uint64_t* out);
 /* ifft: INTT then undo the coset shift (:85-102,165-174); evals has exactly `size` entries */
 void to_domain_ifft(const uint64_t* evals, size_t size, uint64_t shift, uint64_t* out);

@@ -28,8 +28,8 @@ static EncodeTiledFn encode_fn() {
 static int g_l2promo = -1;
 
 // 5-D view of `batch` row-major [4096][ncols] u32 matrices: {column, d0, d1, d2, batch} with row d = 256 d2 + 16 d1 + d0;
-// one box = 8 columns x 16 d0 x one d1 x 16 d2 = a 256-row chunk in the order round 1 reads it
-static int make_map(const uint32_t* in, size_t ncols, size_t batch, size_t batch_stride, CUtensorMap* out) {
+// one box = C columns x 16 d0 x one d1 x 16 d2 = a 256-row chunk in the order round 1 reads it
+static int make_map(const uint32_t* in, size_t ncols, size_t batch, size_t batch_stride, int cols, CUtensorMap* out) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return (int)cudaErrorNotSupported;
     if (g_l2promo < 0) {
@@ -39,7 +39,7 @@ static int make_map(const uint32_t* in, size_t ncols, size_t batch, size_t batch
     const cuuint64_t row = (cuuint64_t)ncols * 4u;
     cuuint64_t dims[5] = {(cuuint64_t)ncols, 16, 16, 16, (cuuint64_t)batch};
     cuuint64_t strides[4] = {row, 16 * row, 256 * row, batch > 1 ? (cuuint64_t)batch_stride * 4u : (cuuint64_t)V7_R * row};
-    cuuint32_t box[5] = {V7_C, 16, 1, 16, 1};
+    cuuint32_t box[5] = {(cuuint32_t)cols, 16, 1, 16, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUtensorMapL2promotion promo = g_l2promo == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                    : g_l2promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
@@ -51,26 +51,28 @@ static int make_map(const uint32_t* in, size_t ncols, size_t batch, size_t batch
 }
 
 struct MapKey {
-    int dev;
+    int dev, cols;
     const void* in;
     size_t ncols, batch, stride;
-    bool operator<(const MapKey& o) const { return std::tie(dev, in, ncols, batch, stride) < std::tie(o.dev, o.in, o.ncols, o.batch, o.stride); }
+    bool operator<(const MapKey& o) const {
+        return std::tie(dev, cols, in, ncols, batch, stride) < std::tie(o.dev, o.cols, o.in, o.ncols, o.batch, o.stride);
+    }
 };
 
 // Descriptors live in device memory, one immutable 128-byte entry per distinct (buffer, shape): the kernel gets a pointer.
 // (A descriptor passed by value in the parameter space can share its address with the different descriptor of the
 // kernel launched just before it; entries here are written once, before their first use, and never change.)
-static int map_get(const uint32_t* in, size_t ncols, size_t batch, size_t stride, const CUtensorMap** out) {
+static int map_get(const uint32_t* in, size_t ncols, size_t batch, size_t stride, int cols, const CUtensorMap** out) {
     static std::mutex mu;
     static std::map<MapKey, CUtensorMap*> cache;
     int dev = 0;
     cudaGetDevice(&dev);
-    const MapKey key{dev, in, ncols, batch, stride};
+    const MapKey key{dev, cols, in, ncols, batch, stride};
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
     if (it == cache.end()) {
         alignas(64) CUtensorMap m;
-        int rc = make_map(in, ncols, batch, stride, &m);
+        int rc = make_map(in, ncols, batch, stride, cols, &m);
         if (rc) return rc;
         CUtensorMap* d = nullptr;
         cudaError_t e = cudaMalloc(&d, sizeof(CUtensorMap));
@@ -84,48 +86,53 @@ static int map_get(const uint32_t* in, size_t ncols, size_t batch, size_t stride
 
 extern int g_pdl;
 
-int launch_pass_v7(bool pass2, const uint32_t* in, size_t ncols, size_t batch, size_t in_batch_stride, V7Params p, bool pdl, cudaStream_t s) {
-    const CUtensorMap* map = nullptr;
-    int rc = map_get(in, ncols, batch, in_batch_stride, &map);
-    if (rc) return rc;
-    static int n_sm[64] = {};
+template <bool PASS2, int C>
+static int launch_one(const CUtensorMap* map, V7Params p, size_t ncols, size_t batch, bool pdl, cudaStream_t s) {
+    using T = V7<C>;
+    static int n_ctas[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (n_sm[dev] == 0) {
-        cudaError_t e = cudaFuncSetAttribute(ntt_pass_v7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V7_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ntt_pass_v7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V7_SMEM);
+    if (n_ctas[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(ntt_pass_v7_kernel<PASS2, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
         if (e != cudaSuccess) return (int)e;
-        cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+        int n_sm = 0, occ = 0;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ntt_pass_v7_kernel<PASS2, C>, T::NT, T::SMEM);
+        if (occ < 1) return (int)cudaErrorLaunchOutOfResources;
+        n_ctas[dev] = n_sm * occ;
     }
-    static int flags = -1;
-    if (flags < 0) {
-        const char* e = getenv("TOYNI_V7_FLAGS");
-        flags = e ? atoi(e) : 0;
-    }
-    p.flags = (uint32_t)flags;
-    static int skew = -1;
-    if (skew < 0) {
-        const char* e = getenv("TOYNI_V7_SKEW");
-        skew = e ? atoi(e) : 0;
-    }
-    p.skew = (uint32_t)skew;
-    p.tiles_x = (uint32_t)(ncols / V7_C);
+    p.tiles_x = (uint32_t)(ncols / C);
     p.total_tiles = (uint32_t)(p.tiles_x * batch);
-    uint32_t ctas = (uint32_t)n_sm[dev];
+    uint32_t ctas = (uint32_t)n_ctas[dev];
     if (ctas > p.total_tiles) ctas = p.total_tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
-    cfg.blockDim = dim3(V7_NT);
-    cfg.dynamicSmemBytes = V7_SMEM;
+    cfg.blockDim = dim3(T::NT);
+    cfg.dynamicSmemBytes = T::SMEM;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = (g_pdl && pdl) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = pass2 ? cudaLaunchKernelEx(&cfg, ntt_pass_v7_kernel<true>, map, p) : cudaLaunchKernelEx(&cfg, ntt_pass_v7_kernel<false>, map, p);
-    return (int)e;
+    return (int)cudaLaunchKernelEx(&cfg, ntt_pass_v7_kernel<PASS2, C>, map, p);
+}
+
+int launch_pass_v7(bool pass2, const uint32_t* in, size_t ncols, size_t batch, size_t in_batch_stride, V7Params p, bool pdl, cudaStream_t s) {
+    static int cols = -1, flags = -1;
+    if (cols < 0) {
+        const char* e = getenv("TOYNI_V7_COLS");
+        cols = (e && atoi(e) == 4) ? 4 : 8;
+        const char* f = getenv("TOYNI_V7_FLAGS");
+        flags = f ? atoi(f) : 0;
+    }
+    p.flags = (uint32_t)flags;
+    const CUtensorMap* map = nullptr;
+    int rc = map_get(in, ncols, batch, in_batch_stride, cols, &map);
+    if (rc) return rc;
+    if (cols == 4) return pass2 ? launch_one<true, 4>(map, p, ncols, batch, pdl, s) : launch_one<false, 4>(map, p, ncols, batch, pdl, s);
+    return pass2 ? launch_one<true, 8>(map, p, ncols, batch, pdl, s) : launch_one<false, 8>(map, p, ncols, batch, pdl, s);
 }
 
 }  // namespace bb
