@@ -216,6 +216,36 @@ int toyni_fri_fold_ext(const uint64_t* evals, size_t m, const uint64_t* xs, cons
 int toyni_merkle_commit(const uint64_t* values, size_t n, int limbs, const uint8_t* salts, uint8_t* nodes_out,
                         uint8_t root_out[32]);
 
+/* ------------------------------------------------------------------------------------------
+ * 4. The sharded paths from ONE host process over the G GPUs of a box (devices 0 .. G-1, G a power of two <= 8).
+ *    The reference has no multi-GPU code; these are the entry points a Rust host binds for SURVEY 8e.  bb_mg_init
+ *    enables peer access between all pairs: the kernels of one GPU store straight into buffers of another
+ *    (NVLink / NVSwitch), devices are ordered by CUDA events on one stream per device — no NCCL, no host
+ *    synchronisation inside a transform.  Calls return once the work is queued; bb_mg_sync waits for it.
+ * ---------------------------------------------------------------------------------------- */
+int bb_mg_init(int ngpus, void** mg_out);
+void bb_mg_destroy(void* mg);
+int bb_mg_ngpus(void* mg);
+int bb_mg_sync(void* mg);
+void* bb_mg_stream(void* mg, int device);   /* the cudaStream_t the layer uses on that device */
+/* ONE 2^log_n transform over the G devices (four-step, n = n1 n2 with log2 n1 = ceil(log_n / 2)).  d_blocks[r] (on
+ * device r) holds column block r of the row-major n1 x n2 input matrix, i.e. (n1, n2/G) words, and is destroyed;
+ * d_outs[r] (on device r, (n1/G) x n2 words) receives out[k1_local][k2] = X[k1 + n1 k2], k1 = r n1/G + k1_local.  The
+ * inter-half twiddle and the transpose run inside the last pass of the column transforms, which stores each row into
+ * d_outs[owner] directly. */
+int bb_mg_ntt_fourstep(void* mg, uint32_t log_n, int dir, uint32_t* const* d_blocks, uint32_t* const* d_outs);
+/* Independent 2^log_n-point columns, ncols[r] of them back to back at d_cols[r] on device r, in place; no exchange. */
+int bb_mg_ntt_batch(void* mg, uint32_t log_n, int dir, uint32_t* const* d_cols, const size_t* ncols);
+/* FRI fold chain (src/math/fri.rs:7-48 layer after layer, x squared per layer as src/fibonacci.rs:228-231) on cyclic
+ * shards: d_shards[r] holds the values i = r (mod G) of the 2^log_m codeword on shift * <w>; folds while the layer has
+ * more than final_size values and its fold partner is still on the same device (m/2 >= G).  betas: limbs words per
+ * fold.  d_layers_out[r] receives the local parts of layers 1, 2, ... back to back; *folds_out the number of folds. */
+int bb_mg_fri_chain(void* mg, uint32_t log_m, uint32_t shift, int limbs, size_t final_size, const uint32_t* betas,
+                    const uint32_t* const* d_shards, uint32_t* const* d_layers_out, size_t* folds_out);
+/* Host-pointer form of the sharded transform: 2^log_n canonical u64 values in natural order, in place (what
+ * ntt_run_inplace does on one device, src/ntt.rs:108): scatter, four-step, gather.  Synchronous. */
+int bb_mg_ntt_host(void* mg, uint64_t* h_data, uint32_t log_n, int dir);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,72 +1,13 @@
-// src/ntt.rs — drop-in replacement for the reference file of the same name (jonas089/toyni), written against the
-// B200-native library in this repository (include/toyni_ntt_cuda.h).  NOT COMPILED HERE: this image has no Rust
-// toolchain; the same C ABI is exercised from Python (toyni_b200/ntt.py) and by tests/.
+// rust/ntt_cuda.rs — the `mod cuda` block of src/ntt.rs (jonas089/toyni), re-written against the B200-native library of
+// this repository (include/toyni_ntt_cuda.h).  It REPLACES lines 83-315 of the reference's src/ntt.rs (everything from
+// `#[cfg(feature = "cuda")] mod cuda {` to the end of the file); lines 1-81 of that file (the CPU `ntt`, `intt`,
+// `roots_of_unity_domain`) stay exactly as they are and are not carried here.  NOT COMPILED HERE: this image has no Rust
+// toolchain; the same C ABI is exercised from Python (toyni_b200/ntt.py), C++ (toyni_b200/host/toyni.hpp) and by tests/.
 //
-// Public surface kept exactly: `ntt`, `intt`, `roots_of_unity_domain` (CPU, unchanged), and with `--features cuda`
-// `cuda_available`, `ntt_cuda`, `intt_cuda`, `CudaBuffer`.  Added (same feature): `coset_fft_cuda`,
-// `coset_ifft_cuda`, `fri_fold_cuda`, `fri_fold_ext_cuda`, `merkle_commit_cuda`, which the call sites in
+// Public surface kept exactly (`--features cuda`): `cuda_available`, `ntt_cuda`, `intt_cuda`, `CudaBuffer`.  Added (same
+// feature): `coset_fft_cuda`, `coset_ifft_cuda`, `fri_fold_cuda`, `fri_fold_ext_cuda`, `merkle_commit_cuda`, the
+// device-resident prover stages, and the multi-GPU layer `MultiGpu` (header section 4), which the call sites in
 // src/math/domain.rs, src/math/fri.rs and src/fibonacci.rs use behind their existing `use_gpu` flag.
-
-use crate::babybear::BabyBear;
-
-// ── CPU NTT (always available; identical to the reference, src/ntt.rs:14-81) ────────────────
-#[inline]
-fn bit_reverse(mut x: usize, log_n: usize) -> usize {
-    let mut r = 0;
-    for _ in 0..log_n {
-        r = (r << 1) | (x & 1);
-        x >>= 1;
-    }
-    r
-}
-
-pub fn ntt(values: &mut [BabyBear], omega: BabyBear) {
-    let n = values.len();
-    assert!(n.is_power_of_two(), "NTT size must be power of 2");
-    let log_n = n.trailing_zeros() as usize;
-    for i in 0..n {
-        let j = bit_reverse(i, log_n);
-        if i < j {
-            values.swap(i, j);
-        }
-    }
-    let mut len = 2;
-    while len <= n {
-        let w_len = omega.pow((n / len) as u64);
-        for i in (0..n).step_by(len) {
-            let mut w = BabyBear::one();
-            for j in 0..len / 2 {
-                let u = values[i + j];
-                let v = values[i + j + len / 2] * w;
-                values[i + j] = u + v;
-                values[i + j + len / 2] = u - v;
-                w = w * w_len;
-            }
-        }
-        len *= 2;
-    }
-}
-
-pub fn intt(values: &mut [BabyBear], omega: BabyBear) {
-    let n = values.len();
-    ntt(values, omega.pow(n as u64 - 1));
-    let inv_n = BabyBear::new(n as u64).inverse();
-    for v in values.iter_mut() {
-        *v = *v * inv_n;
-    }
-}
-
-pub fn roots_of_unity_domain(n: usize) -> Vec<BabyBear> {
-    assert!(n.is_power_of_two(), "Domain size must be power of 2");
-    let omega = BabyBear::get_root_of_unity(n.trailing_zeros());
-    let mut domain = Vec::with_capacity(n);
-    let mut cur = BabyBear::one();
-    for _ in 0..n {
-        domain.push(cur);
-        cur = cur * omega;
-    }
-    domain
-}
 
 // ── CUDA path (feature = "cuda") ─────────────────────────────────────────────────────────────
 #[cfg(feature = "cuda")]
@@ -91,6 +32,9 @@ mod cuda {
         fn ntt_ctx_create(n: u32) -> *mut c_void;
         fn ntt_run_inplace(ctx: *mut c_void, h_data: *mut u64);
         fn intt_run_inplace(ctx: *mut c_void, h_data: *mut u64);
+        // the same transforms with the outcome as a return value (the void forms above cannot report a failed launch)
+        fn ntt_run_inplace_rc(ctx: *mut c_void, h_data: *mut u64) -> CudaError;
+        fn intt_run_inplace_rc(ctx: *mut c_void, h_data: *mut u64) -> CudaError;
         // new in the B200 library (include/toyni_ntt_cuda.h, sections 2-3)
         fn bb_last_error() -> CudaError;
         fn bb_clear_error();
@@ -113,6 +57,15 @@ mod cuda {
         fn bb_merkle_open_batch_device(d_nodes: *const u8, nleaves: usize, indices: *const u64, nq: usize, paths_out: *mut u8,
                                        pos_out: *mut u8, depth_out: *mut usize) -> CudaError;
         fn bb_gather_device(d_src: *const c_void, elem_bytes: usize, indices: *const u64, nq: usize, out: *mut c_void) -> CudaError;
+        // one process, G devices (header section 4)
+        fn bb_mg_init(ngpus: i32, mg_out: *mut *mut c_void) -> CudaError;
+        fn bb_mg_destroy(mg: *mut c_void);
+        fn bb_mg_sync(mg: *mut c_void) -> CudaError;
+        fn bb_mg_ntt_fourstep(mg: *mut c_void, log_n: u32, dir: i32, d_blocks: *const *mut u32, d_outs: *const *mut u32) -> CudaError;
+        fn bb_mg_ntt_batch(mg: *mut c_void, log_n: u32, dir: i32, d_cols: *const *mut u32, ncols: *const usize) -> CudaError;
+        fn bb_mg_fri_chain(mg: *mut c_void, log_m: u32, shift: u32, limbs: i32, final_size: usize, betas: *const u32,
+                           d_shards: *const *const u32, d_layers_out: *const *mut u32, folds_out: *mut usize) -> CudaError;
+        fn bb_mg_ntt_host(mg: *mut c_void, h_data: *mut u64, log_n: u32, dir: i32) -> CudaError;
     }
 
     // BabyBear is `#[repr(C)] { value: u64 }` and Ext is `#[repr(C)] { c: [BabyBear; 4] }`
@@ -205,13 +158,11 @@ mod cuda {
         assert!(n.trailing_zeros() <= 27, "BabyBear only supports NTT up to 2^27");
         let ctx = get_or_create_ctx(n)?;
         let raw = values.as_mut_ptr() as *mut u64;
-        unsafe {
-            bb_clear_error();
-            if inverse { intt_run_inplace(ctx, raw) } else { ntt_run_inplace(ctx, raw) }
-            match bb_last_error() {
-                CUDA_SUCCESS => Ok(()),
-                e => Err(format!("CUDA NTT failed: {}", err_string(e))),
-            }
+        // the reference calls the void `ntt_run_inplace` / `intt_run_inplace` (src/ntt.rs:233,248), which cannot fail
+        // visibly; the `_rc` forms return the first CUDA error of the call
+        match unsafe { if inverse { intt_run_inplace_rc(ctx, raw) } else { ntt_run_inplace_rc(ctx, raw) } } {
+            CUDA_SUCCESS => Ok(()),
+            e => Err(format!("CUDA NTT failed: {}", err_string(e))),
         }
     }
 
@@ -257,14 +208,57 @@ mod cuda {
         ck(unsafe { toyni_fri_fold_ext(evals.as_ptr() as *const u64, evals.len(), xs.as_ptr() as *const u64, beta.c.as_ptr() as *const u64, out.as_mut_ptr() as *mut u64) }, "CUDA fold")?;
         Ok(out)
     }
-    /// build_merkle_tree / build_unsalted_tree (src/fibonacci.rs:340-363): every level, leaf level first, 32 B each.
-    pub fn merkle_commit_cuda(evals: &[BabyBear], salts: Option<&[[u8; 16]]>) -> Result<(Vec<u8>, [u8; 32]), String> {
+    /// build_merkle_tree / build_unsalted_tree (src/fibonacci.rs:340-363).  `want_nodes` = false returns only the root
+    /// (no 2 GiB download at 2^25 leaves; openings then come from `merkle_open_batch_cuda` on the device-resident tree);
+    /// true returns every level, leaf level first, 32 B each.
+    pub fn merkle_commit_cuda(evals: &[BabyBear], salts: Option<&[[u8; 16]]>, want_nodes: bool) -> Result<(Vec<u8>, [u8; 32]), String> {
         let n = evals.len();
-        let mut nodes = vec![0u8; unsafe { bb_merkle_node_count(n) } * 32];
+        let mut nodes = if want_nodes { vec![0u8; unsafe { bb_merkle_node_count(n) } * 32] } else { Vec::new() };
         let mut root = [0u8; 32];
         let sp = salts.map(|s| s.as_ptr() as *const u8).unwrap_or(std::ptr::null());
-        ck(unsafe { toyni_merkle_commit(evals.as_ptr() as *const u64, n, 1, sp, nodes.as_mut_ptr(), root.as_mut_ptr()) }, "CUDA Merkle commit")?;
+        let np = if want_nodes { nodes.as_mut_ptr() } else { std::ptr::null_mut() };
+        ck(unsafe { toyni_merkle_commit(evals.as_ptr() as *const u64, n, 1, sp, np, root.as_mut_ptr()) }, "CUDA Merkle commit")?;
         Ok((nodes, root))
+    }
+
+    /// The sharded paths over the G GPUs of one box, driven from this process (header section 4).
+    pub struct MultiGpu {
+        h: *mut c_void,
+    }
+    unsafe impl Send for MultiGpu {}
+    impl MultiGpu {
+        pub fn new(ngpus: usize) -> Result<Self, String> {
+            let mut h = std::ptr::null_mut();
+            ck(unsafe { bb_mg_init(ngpus as i32, &mut h) }, "bb_mg_init")?;
+            Ok(Self { h })
+        }
+        /// One 2^log_n NTT over all devices, natural order in and out on the host (scatter, four-step, gather).
+        pub fn ntt(&self, values: &mut [BabyBear], inverse: bool) -> Result<(), String> {
+            let n = values.len();
+            assert!(n.is_power_of_two() && n.trailing_zeros() <= 27, "NTT size must be a power of 2 up to 2^27");
+            ck(unsafe { bb_mg_ntt_host(self.h, values.as_mut_ptr() as *mut u64, n.trailing_zeros(), inverse as i32) }, "multi-GPU NTT")
+        }
+        /// Device-resident forms: column blocks in, result slabs out (see the header for the layouts).
+        pub fn ntt_fourstep(&self, log_n: u32, inverse: bool, d_blocks: &[*mut u32], d_outs: &[*mut u32]) -> Result<(), String> {
+            ck(unsafe { bb_mg_ntt_fourstep(self.h, log_n, inverse as i32, d_blocks.as_ptr(), d_outs.as_ptr()) }, "multi-GPU four-step NTT")
+        }
+        pub fn ntt_batch(&self, log_n: u32, inverse: bool, d_cols: &[*mut u32], ncols: &[usize]) -> Result<(), String> {
+            ck(unsafe { bb_mg_ntt_batch(self.h, log_n, inverse as i32, d_cols.as_ptr(), ncols.as_ptr()) }, "multi-GPU batched NTT")
+        }
+        /// Fold chain on cyclic shards (betas: `limbs` words per fold); returns the number of folds done.
+        pub fn fri_chain(&self, log_m: u32, shift: BabyBear, limbs: usize, final_size: usize, betas: &[u32], d_shards: &[*const u32],
+                         d_layers_out: &[*mut u32]) -> Result<usize, String> {
+            let mut folds = 0usize;
+            ck(unsafe { bb_mg_fri_chain(self.h, log_m, shift.value as u32, limbs as i32, final_size, betas.as_ptr(), d_shards.as_ptr(),
+                                        d_layers_out.as_ptr(), &mut folds) }, "multi-GPU fold chain")?;
+            Ok(folds)
+        }
+        pub fn sync(&self) -> Result<(), String> { ck(unsafe { bb_mg_sync(self.h) }, "bb_mg_sync") }
+    }
+    impl Drop for MultiGpu {
+        fn drop(&mut self) {
+            unsafe { bb_mg_destroy(self.h) }
+        }
     }
 
     /// Device-resident column of the shifted domain (u32 per element): what `generate_proof` keeps in HBM between the
@@ -319,5 +313,5 @@ mod cuda {
 pub use cuda::{
     coset_fft_cuda, coset_fft_ext_cuda, coset_ifft_cuda, coset_ifft_ext_cuda, cuda_available, fri_fold_cuda,
     fib_constraint_cuda, fib_deep_cuda, fib_quotient_cuda, fri_fold_ext_cuda, gather_cuda, intt_cuda, merkle_commit_cuda,
-    merkle_open_batch_cuda, ntt_cuda, poly_eval_cuda, CudaBuffer, DeviceColumn,
+    merkle_open_batch_cuda, ntt_cuda, poly_eval_cuda, CudaBuffer, DeviceColumn, MultiGpu,
 };

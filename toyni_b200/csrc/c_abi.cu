@@ -59,6 +59,23 @@ static inline unsigned conv_blocks(size_t n) {
 }
 
 extern "C" {
+static int run_ntt(const uint32_t* in, uint32_t* out, uint32_t log_n, int log_inner, size_t n_in, size_t batch, int dir,
+                   uint32_t shift, const FourStepScatter* scatter = nullptr);
+}
+// what the multi-device layer (mg.cu) needs from this file
+namespace bb {
+namespace abi {
+int note_error(int rc) { return note(rc); }
+cudaStream_t get_stream() { return g_stream; }
+void set_stream(cudaStream_t s) { g_stream = s; }
+void count_launches(unsigned n) { g_launches += n; }
+int ntt(const uint32_t* in, uint32_t* out, uint32_t log_n, int log_inner, size_t n_in, size_t batch, int dir, const FourStepScatter* scatter) {
+    return run_ntt(in, out, log_n, log_inner, n_in, batch, dir, 1, scatter);
+}
+}  // namespace abi
+}  // namespace bb
+
+extern "C" {
 
 // ================================================================== 1. reference symbols
 int cuda_malloc(uint64_t** d_ptr, size_t count) { return note((int)cudaMalloc((void**)d_ptr, count * sizeof(uint64_t))); }
@@ -198,7 +215,7 @@ int bb_widen_u32_to_u64(const uint32_t* d_src, uint64_t* d_dst, size_t count) {
 }
 
 static int run_ntt(const uint32_t* in, uint32_t* out, uint32_t log_n, int log_inner, size_t n_in, size_t batch, int dir,
-                   uint32_t shift, const FourStepScatter* scatter = nullptr) {
+                   uint32_t shift, const FourStepScatter* scatter) {
     if (log_n > (uint32_t)MAX_LOG_N || (dir != 0 && dir != 1)) return note((int)cudaErrorInvalidValue);
     if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
     NttDesc d{};

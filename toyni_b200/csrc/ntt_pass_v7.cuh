@@ -47,7 +47,9 @@ struct V7 {
     static constexpr uint32_t OFF_U = OFF_A + 16 * C * 8;    // U[k][c]   plain
     static constexpr uint32_t OFF_V = OFF_U + 16 * C * 4;    // V[r][c]   Montgomery form (carries the scale)
     static constexpr uint32_t OFF_BAR = OFF_V + 16 * C * 4;  // one mbarrier per warp
-    static constexpr uint32_t SMEM = OFF_BAR + WARPS * 8;
+    static constexpr uint32_t STAGE = 128 * RB;              // per warp: half a chunk of results on its way out (TMA store)
+    static constexpr uint32_t OFF_STAGE = (OFF_BAR + WARPS * 8 + 127u) & ~127u;
+    static constexpr uint32_t SMEM = OFF_STAGE + WARPS * STAGE;
     // physical q0 of position (q1, q2, q0) is q0 ^ swz(q2): the strided round-1 stores (row stride 16) then spread over
     // all banks — a quarter warp covers 128 bytes = 4 rows of 32 bytes (C = 8) or 8 rows of 16 bytes (C = 4)
     __host__ __device__ static constexpr uint32_t swz(uint32_t q2) { return q2 & (C == 8 ? 3u : 7u); }
@@ -94,6 +96,11 @@ BB_D void v7_mbar_wait(uint32_t bar, uint32_t parity, uint32_t* err, uint32_t co
             __trap();
         }
     }
+}
+BB_D void v7_tma_store_5d(const CUtensorMap* map, uint32_t src, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];\n" ::"l"(map), "r"(src), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
 }
 BB_D void v7_tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t c4) {
     asm volatile(
@@ -221,8 +228,8 @@ BB_D void v7_round2(uint8_t* smem, uint32_t flags, uint32_t q2, const V7Lane<C>&
 // round 3 of this lane's chunk of tile `tile`; once the warp's chunk(s) sit in registers lane 0 re-fills the region with
 // the same chunk(s) of tile `next` (if any) and the copy travels during the arithmetic and the stores below
 template <bool PASS2, int C>
-BB_D void v7_round3(uint8_t* smem, const V7Params& p, const CUtensorMap* tmap, uint32_t tile, uint32_t next, const V7Lane<C>& ln, uint32_t warp,
-                    uint32_t lane, uint32_t bar) {
+BB_D void v7_round3(uint8_t* smem, const V7Params& p, const CUtensorMap* tmap, const CUtensorMap* omap, uint32_t tile, uint32_t next,
+                    const V7Lane<C>& ln, uint32_t warp, uint32_t lane, uint32_t bar) {
     using T = V7<C>;
     uint4 x[16];
     const uint32_t r = ln.r, kc = ln.kc;
@@ -259,7 +266,7 @@ BB_D void v7_round3(uint8_t* smem, const V7Params& p, const CUtensorMap* tmap, u
             bfly4(x[k], x[k + (1 << t)], tws[(256 * kp) << (3 - t)]);
         }
     }
-    if (p.flags & 8u) {  // diagnostic: no global stores (one predicated-off store keeps the results live)
+    if ((p.flags & 8u) || (p.flags & (PASS2 ? 64u : 32u))) {  // diagnostic: no global stores (one predicated-off store keeps the results live)
         uint32_t acc = 0;
 #pragma unroll
         for (int k = 0; k < 16; k++) acc ^= x[k].x ^ x[k].y ^ x[k].z ^ x[k].w;
@@ -269,6 +276,31 @@ BB_D void v7_round3(uint8_t* smem, const V7Params& p, const CUtensorMap* tmap, u
     const uint32_t bz = tile / p.tiles_x, tx = tile - bz * p.tiles_x;
     const uint32_t col = tx * C + (ln.cq >> 2);
     uint32_t* out = p.out + (size_t)bz * p.out_batch_stride;
+    if constexpr (PASS2 && C == 8) {
+        if (omap) {
+            // Row store through the TMA: the chunk's 256 result rows (32 bytes each, 16 KB apart in global memory) leave as
+            // two boxes {8 columns, 16 x e0, e1 = kc, 8 x e2} from a per-warp staging buffer, so the scattered 32-byte
+            // segments cost no LSU / L1 store slots (16 STG.128 per lane, 16 sectors each, were 13 us of a transform).
+            uint8_t* stage = smem + T::OFF_STAGE + warp * T::STAGE;
+            const uint32_t stage_s = smem_u32(stage);
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // previous tile's boxes have left
+            __syncwarp();
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) *reinterpret_cast<uint4*>(stage + (k * 16u + r) * T::RB + ln.cq) = canon4(x[8 * half + k]);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the TMA
+                __syncwarp();
+                if (lane == 0) {
+                    v7_tma_store_5d(omap, stage_s, tx * C, 0u, kc, 8u * half, bz);
+                    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                    if (half == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+                }
+                __syncwarp();
+            }
+            return;
+        }
+    }
     if constexpr (PASS2) {
         const uint32_t j = col >> p.log_pfull, low = col & ((1u << p.log_pfull) - 1u);
         uint32_t* o = out + ((((size_t)j << V7_LR) + b) << p.log_pfull) + low;
@@ -291,7 +323,7 @@ BB_D void v7_round3(uint8_t* smem, const V7Params& p, const CUtensorMap* tmap, u
 }
 
 template <bool PASS2, int C>
-__global__ void __launch_bounds__(V7<C>::NT, V7<C>::CTAS_PER_SM) ntt_pass_v7_kernel(const CUtensorMap* __restrict__ tmap, const V7Params p) {
+__global__ void __launch_bounds__(V7<C>::NT, V7<C>::CTAS_PER_SM) ntt_pass_v7_kernel(const CUtensorMap* __restrict__ tmap, const CUtensorMap* __restrict__ omap, const V7Params p) {
     using T = V7<C>;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
@@ -333,7 +365,7 @@ __global__ void __launch_bounds__(V7<C>::NT, V7<C>::CTAS_PER_SM) ntt_pass_v7_ker
     __syncthreads();
     while (true) {
         const bool have_next = next < p.total_tiles;
-        if (have_cur) v7_round3<PASS2, C>(smem, p, tmap, cur, next, ln, warp, lane, bar);
+        if (have_cur) v7_round3<PASS2, C>(smem, p, tmap, omap, cur, next, ln, warp, lane, bar);
         if (!have_next) break;
         if (!(p.flags & 2u)) v7_mbar_wait(bar, it & 1u, p.err, 0x60000000u | (it << 4) | warp);
         v7_round1<PASS2, C>(smem, p, ln);
@@ -349,6 +381,7 @@ __global__ void __launch_bounds__(V7<C>::NT, V7<C>::CTAS_PER_SM) ntt_pass_v7_ker
         next = nn;
         it++;
     }
+    if (PASS2 && omap && lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // the last boxes are in global memory
 }
 
 }  // namespace bb

@@ -29,7 +29,7 @@ static int g_l2promo = -1;
 
 // 5-D view of `batch` row-major [4096][ncols] u32 matrices: {column, d0, d1, d2, batch} with row d = 256 d2 + 16 d1 + d0;
 // one box = C columns x 16 d0 x one d1 x 16 d2 = a 256-row chunk in the order round 1 reads it
-static int make_map(const uint32_t* in, size_t ncols, size_t batch, size_t batch_stride, int cols, CUtensorMap* out) {
+static int make_map(const uint32_t* in, size_t ncols, size_t batch, size_t batch_stride, int cols, int box_d2, CUtensorMap* out) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return (int)cudaErrorNotSupported;
     if (g_l2promo < 0) {
@@ -39,7 +39,7 @@ static int make_map(const uint32_t* in, size_t ncols, size_t batch, size_t batch
     const cuuint64_t row = (cuuint64_t)ncols * 4u;
     cuuint64_t dims[5] = {(cuuint64_t)ncols, 16, 16, 16, (cuuint64_t)batch};
     cuuint64_t strides[4] = {row, 16 * row, 256 * row, batch > 1 ? (cuuint64_t)batch_stride * 4u : (cuuint64_t)V7_R * row};
-    cuuint32_t box[5] = {(cuuint32_t)cols, 16, 1, 16, 1};
+    cuuint32_t box[5] = {(cuuint32_t)cols, 16, 1, (cuuint32_t)box_d2, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUtensorMapL2promotion promo = g_l2promo == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                    : g_l2promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
@@ -51,28 +51,28 @@ static int make_map(const uint32_t* in, size_t ncols, size_t batch, size_t batch
 }
 
 struct MapKey {
-    int dev, cols;
+    int dev, cols, box_d2;
     const void* in;
     size_t ncols, batch, stride;
     bool operator<(const MapKey& o) const {
-        return std::tie(dev, cols, in, ncols, batch, stride) < std::tie(o.dev, o.cols, o.in, o.ncols, o.batch, o.stride);
+        return std::tie(dev, cols, box_d2, in, ncols, batch, stride) < std::tie(o.dev, o.cols, o.box_d2, o.in, o.ncols, o.batch, o.stride);
     }
 };
 
 // Descriptors live in device memory, one immutable 128-byte entry per distinct (buffer, shape): the kernel gets a pointer.
 // (A descriptor passed by value in the parameter space can share its address with the different descriptor of the
 // kernel launched just before it; entries here are written once, before their first use, and never change.)
-static int map_get(const uint32_t* in, size_t ncols, size_t batch, size_t stride, int cols, const CUtensorMap** out) {
+static int map_get(const uint32_t* in, size_t ncols, size_t batch, size_t stride, int cols, int box_d2, const CUtensorMap** out) {
     static std::mutex mu;
     static std::map<MapKey, CUtensorMap*> cache;
     int dev = 0;
     cudaGetDevice(&dev);
-    const MapKey key{dev, cols, in, ncols, batch, stride};
+    const MapKey key{dev, cols, box_d2, in, ncols, batch, stride};
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
     if (it == cache.end()) {
         alignas(64) CUtensorMap m;
-        int rc = make_map(in, ncols, batch, stride, cols, &m);
+        int rc = make_map(in, ncols, batch, stride, cols, box_d2, &m);
         if (rc) return rc;
         CUtensorMap* d = nullptr;
         cudaError_t e = cudaMalloc(&d, sizeof(CUtensorMap));
@@ -87,7 +87,7 @@ static int map_get(const uint32_t* in, size_t ncols, size_t batch, size_t stride
 extern int g_pdl;
 
 template <bool PASS2, int C>
-static int launch_one(const CUtensorMap* map, V7Params p, size_t ncols, size_t batch, bool pdl, cudaStream_t s) {
+static int launch_one(const CUtensorMap* map, const CUtensorMap* omap, V7Params p, size_t ncols, size_t batch, bool pdl, cudaStream_t s) {
     using T = V7<C>;
     static int n_ctas[64] = {};
     int dev = 0;
@@ -116,7 +116,7 @@ static int launch_one(const CUtensorMap* map, V7Params p, size_t ncols, size_t b
     attr[0].val.programmaticStreamSerializationAllowed = (g_pdl && pdl) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, ntt_pass_v7_kernel<PASS2, C>, map, p);
+    return (int)cudaLaunchKernelEx(&cfg, ntt_pass_v7_kernel<PASS2, C>, map, omap, p);
 }
 
 int launch_pass_v7(bool pass2, const uint32_t* in, size_t ncols, size_t batch, size_t in_batch_stride, V7Params p, bool pdl, cudaStream_t s) {
@@ -129,10 +129,21 @@ int launch_pass_v7(bool pass2, const uint32_t* in, size_t ncols, size_t batch, s
     }
     p.flags = (uint32_t)flags;
     const CUtensorMap* map = nullptr;
-    int rc = map_get(in, ncols, batch, in_batch_stride, cols, &map);
+    int rc = map_get(in, ncols, batch, in_batch_stride, cols, 16, &map);
     if (rc) return rc;
-    if (cols == 4) return pass2 ? launch_one<true, 4>(map, p, ncols, batch, pdl, s) : launch_one<false, 4>(map, p, ncols, batch, pdl, s);
-    return pass2 ? launch_one<true, 8>(map, p, ncols, batch, pdl, s) : launch_one<false, 8>(map, p, ncols, batch, pdl, s);
+    // last pass of the square plan (out[e * ncols + col]): the result rows leave through the TMA as well
+    const CUtensorMap* omap = nullptr;
+    static int tma_store = -1;
+    if (tma_store < 0) {
+        const char* e = getenv("TOYNI_V7_TMA_STORE");
+        tma_store = e ? atoi(e) : 1;
+    }
+    if (pass2 && cols == 8 && tma_store && ((size_t)1 << p.log_pfull) == ncols && (batch == 1 || p.out_batch_stride % 4 == 0)) {
+        rc = map_get(p.out, ncols, batch, (size_t)p.out_batch_stride, cols, 8, &omap);
+        if (rc) return rc;
+    }
+    if (cols == 4) return pass2 ? launch_one<true, 4>(map, omap, p, ncols, batch, pdl, s) : launch_one<false, 4>(map, omap, p, ncols, batch, pdl, s);
+    return pass2 ? launch_one<true, 8>(map, omap, p, ncols, batch, pdl, s) : launch_one<false, 8>(map, omap, p, ncols, batch, pdl, s);
 }
 
 }  // namespace bb

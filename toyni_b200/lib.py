@@ -86,6 +86,17 @@ _SIGNATURES = {
     "toyni_fri_fold": ([C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p], C.c_int),
     "toyni_fri_fold_ext": ([C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
     "toyni_merkle_commit": ([C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+    # section 4: one process, G devices
+    "bb_mg_init": ([C.c_int, C.POINTER(C.c_void_p)], C.c_int),
+    "bb_mg_destroy": ([C.c_void_p], None),
+    "bb_mg_ngpus": ([C.c_void_p], C.c_int),
+    "bb_mg_sync": ([C.c_void_p], C.c_int),
+    "bb_mg_stream": ([C.c_void_p, C.c_int], C.c_void_p),
+    "bb_mg_ntt_fourstep": ([C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)], C.c_int),
+    "bb_mg_ntt_batch": ([C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)], C.c_int),
+    "bb_mg_fri_chain": ([C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                         C.POINTER(C.c_size_t)], C.c_int),
+    "bb_mg_ntt_host": ([C.c_void_p, C.c_void_p, C.c_uint32, C.c_int], C.c_int),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
