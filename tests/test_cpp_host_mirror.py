@@ -29,3 +29,18 @@ def test_cpp_host_mirror_runs_the_reference_gpu_tests():
     out = subprocess.run([BIN], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "all C++ host-mirror tests passed" in out.stdout
+
+
+def test_cpp_proof_format_round_trips_an_oracle_proof(tmp_path):
+    """toyni.hpp's StarkProof reads the canonical bytes of a proof made by the oracle prover and writes the same bytes back
+    (the C++ counterpart of toyni_b200/proof.py; the reference has no serialization, src/fibonacci.rs:62-86)."""
+    from oracle import fibonacci as F
+    exe = os.path.join(ROOT, "tests", "cpp", "test_proof_format.bin")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "toyni_b200", "host"),
+                           os.path.join(ROOT, "tests", "cpp", "test_proof_format.cpp"), "-o", exe])
+    p = F.generate_proof(F.fibonacci_trace(64), *F.proof_randomness(64), interpolate="intt")
+    path = tmp_path / "proof.bin"
+    path.write_bytes(F.serialize_proof(p))
+    out = subprocess.run([exe, str(path)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "trace_len=64 lde_size=2048 fri_roots=9 final=8 queries=44" in out.stdout and "round trip ok" in out.stdout

@@ -25,6 +25,21 @@ def test_oracle_prover_and_verifier_cpu():
         F.generate_proof(bad_trace, *rnd)
 
 
+def test_product_serializer_matches_the_oracle_format_cpu():
+    """toyni_b200/proof.py (product) against oracle/fibonacci.py::serialize_proof (checker) on an oracle-made proof:
+    same bytes, lossless round trip, truncation and trailing bytes rejected."""
+    from toyni_b200 import proof as product_proof
+    p = F.generate_proof(F.fibonacci_trace(64), *F.proof_randomness(64), interpolate="intt")
+    blob = product_proof.serialize_proof(p)
+    assert blob == F.serialize_proof(p)
+    back = product_proof.deserialize_proof(blob)
+    assert product_proof.serialize_proof(back) == blob and F.verify(back)
+    with pytest.raises(ValueError):
+        product_proof.deserialize_proof(blob[:-1])
+    with pytest.raises(ValueError):
+        product_proof.deserialize_proof(blob + b"\x00")
+
+
 def _tamper_cases(p):  # src/verifier.rs:314-380
     a = copy.deepcopy(p); a["t_z"] = (a["t_z"] + 1) % F.P; yield a
     a = copy.deepcopy(p); a["q_z"] = (a["q_z"] + 1) % F.P; yield a
@@ -65,6 +80,12 @@ def test_gpu_proof_is_byte_identical_and_verifies(trace_len):
     ref = F.generate_proof(tr, *rnd, interpolate="lagrange" if trace_len == 64 else "intt")
     got = prover.generate_proof(tr, *rnd)
     assert F.serialize_proof(got) == F.serialize_proof(ref)
+    # the product's own serializer (toyni_b200/proof.py) emits the same bytes as the oracle's, and reads them back
+    from toyni_b200 import proof as product_proof
+    blob = product_proof.serialize_proof(got)
+    assert blob == F.serialize_proof(ref)
+    assert product_proof.serialize_proof(product_proof.deserialize_proof(blob)) == blob
+    assert F.verify(product_proof.deserialize_proof(blob))
     assert F.verify(got)
     if trace_len == 1 << 10:  # shape of BASELINE config 1
         assert got["lde_size"] == 32768 and len(got["fri_commitments"]) == 12 and len(got["fri_final_layer"]) == 16

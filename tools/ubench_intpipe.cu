@@ -10,9 +10,11 @@
 
 template <int OP>
 __global__ void __launch_bounds__(256) kern(uint32_t* out, uint32_t seed, uint32_t w, uint32_t wp) {
-    uint32_t a[ILP], b[ILP];
+    uint32_t a[ILP], b[ILP], wr[4], wpr[4];
 #pragma unroll
     for (int i = 0; i < ILP; i++) { a[i] = seed + threadIdx.x * 7 + i; b[i] = seed * 3 + i + blockIdx.x; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { wr[i] = w + threadIdx.x * 2654435761u + i; wpr[i] = wp ^ (threadIdx.x * 40503u + i); }  // per-thread values
 #pragma unroll 1
     for (int it = 0; it < ITERS; it++) {
 #pragma unroll
@@ -37,6 +39,16 @@ __global__ void __launch_bounds__(256) kern(uint32_t* out, uint32_t seed, uint32
                 uint32_t m = (uint32_t)t * 2013265919u;
                 uint32_t r = (uint32_t)(t >> 32) - __umulhi(m, P);
                 a[i] = min(r, r + P);
+            }
+            if (OP == 10) { a[i] = a[i] * wr[i & 3] + b[i]; }                          // IMAD, both multiplicands in vector registers
+            if (OP == 11) { a[i] = __umulhi(a[i], wr[i & 3]) + b[i]; }                 // IMAD.HI.U32, both multiplicands in vector registers
+            if (OP == 12) {  // the same butterfly with a PER-THREAD twiddle (w, w') held in vector registers
+                uint32_t q = __umulhi(b[i], wpr[i & 3]);
+                uint32_t v = b[i] * wr[i & 3] - q * P;
+                v = min(v, v - P);
+                uint32_t u = min(a[i], a[i] - P);
+                a[i] = u + v;
+                b[i] = u - v + P;
             }
             if (OP == 9) {  // butterfly with one add moved to the fma pipe (IMAD x*1+y)
                 uint32_t q = __umulhi(b[i], wp);
@@ -89,5 +101,8 @@ int main() {
     run<7>("butterfly(7 instr) per-bfly", 1, sms, mhz);
     run<8>("montmul per-mul", 1, sms, mhz);
     run<9>("butterfly(fma-add) per-bfly", 1, sms, mhz);
+    run<10>("IMAD reg*reg", 1, sms, mhz);
+    run<11>("IMAD.HI.U32 reg*reg", 1, sms, mhz);
+    run<12>("butterfly, per-thread twiddle", 1, sms, mhz);
     return 0;
 }

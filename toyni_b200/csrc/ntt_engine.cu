@@ -398,7 +398,12 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
         lk.unlock();
         return rc ? rc : v7_launch(d, job, stream);
     }
-    const NttPlan pl = plan_locked(d.log_n, d.log_inner, d.batch, false);
+    NttPlan pl = plan_locked(d.log_n, d.log_inner, d.batch, false);
+    if (d.scatter && pl.npass >= 1 && g_plan_override.find(d.log_n) == g_plan_override.end()) {
+        // the scattering pass stores rows of 2^lc values to peer GPUs: 32 columns make them full 128-byte lines on NVLink
+        const int last = pl.npass - 1, lc5 = pick_lc(pl.lr[last], 5);
+        if (d.log_inner >= lc5) pl.lc[last] = lc5;
+    }
 
     const uint32_t n_inv = bb::inv((uint32_t)(n % P));
     uint32_t omega = root_of_unity(d.log_n);

@@ -67,8 +67,8 @@ struct V7Params {
     PowTable tab;                         // w_n^t
     PowTable tab_scaled;                  // w_n^t * scale (n^-1 of an inverse transform, else the same table)
     uint32_t* err;                        // device words for time-outs / diagnostics (may be null)
-    // diagnostics (TOYNI_V7_FLAGS): 1 = skip the butterflies (memory traffic only), 2 = no TMA traffic (arithmetic only);
-    // results are garbage in both modes
+    // diagnostics (TOYNI_V7_FLAGS): 1 = skip the butterflies (memory traffic only), 2 = no TMA loads (arithmetic only),
+    // 8 = no global stores; results are garbage in all three modes (tools/v7_time.py, profiles/v7_decomposition_r2.txt)
     uint32_t flags;
 };
 
@@ -266,7 +266,7 @@ BB_D void v7_round3(uint8_t* smem, const V7Params& p, const CUtensorMap* tmap, c
             bfly4(x[k], x[k + (1 << t)], tws[(256 * kp) << (3 - t)]);
         }
     }
-    if ((p.flags & 8u) || (p.flags & (PASS2 ? 64u : 32u))) {  // diagnostic: no global stores (one predicated-off store keeps the results live)
+    if (p.flags & 8u) {  // diagnostic: no global stores (one predicated-off store keeps the results live)
         uint32_t acc = 0;
 #pragma unroll
         for (int k = 0; k < 16; k++) acc ^= x[k].x ^ x[k].y ^ x[k].z ^ x[k].w;

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "toyni_ntt_cuda.h"
@@ -223,5 +224,143 @@ inline SaltedTree build_merkle_tree(const std::vector<BabyBear>& evals, const st
 }
 /// src/fibonacci.rs:357-363
 inline SaltedTree build_unsalted_tree(const std::vector<BabyBear>& evals) { return commit(evals, nullptr); }
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Proof object and its canonical byte form.  The structs mirror src/fibonacci.rs:44-86; the reference has no
+// serialization (`#[derive(Debug)]` only), so the format is defined by this library (toyni_b200/proof.py is the same
+// format in Python): u64 little-endian integers / field values (src/babybear.rs:53-55), raw 32-byte digests, u64 length
+// prefixes, fields in declaration order; a salt is prefixed by one length byte, a path entry is digest + 1 byte
+// (1 = sibling on the right).
+struct MerkleOpening {  // src/fibonacci.rs:44-51
+    uint64_t index = 0;
+    BabyBear value{0};
+    std::vector<uint8_t> salt;
+    std::vector<std::array<uint8_t, 32>> path;
+    std::vector<bool> position;
+};
+struct QueryProof {  // src/fibonacci.rs:53-60
+    uint64_t index = 0;
+    MerkleOpening deep_opening, deep_opening_pair, trace_opening, trace_opening_g, trace_opening_gg, quotient_opening;
+    std::vector<std::pair<MerkleOpening, MerkleOpening>> fri_openings;
+};
+struct StarkProof {  // src/fibonacci.rs:62-86
+    uint64_t trace_len = 0, lde_size = 0;
+    std::array<uint8_t, 32> trace_commitment{}, quotient_commitment{};
+    BabyBear t_z{0}, t_gz{0}, t_ggz{0}, q_z{0};
+    std::vector<std::array<uint8_t, 32>> fri_commitments;
+    std::vector<BabyBear> fri_final_layer;
+    std::vector<QueryProof> query_proofs;
+};
+
+namespace detail {
+inline void put_u64(std::vector<uint8_t>& out, uint64_t v) {
+    for (int b = 0; b < 8; b++) out.push_back((uint8_t)(v >> (8 * b)));
+}
+inline void put_opening(std::vector<uint8_t>& out, const MerkleOpening& o) {
+    put_u64(out, o.index);
+    put_u64(out, o.value.value);
+    if (o.salt.size() > 255 || o.path.size() != o.position.size()) throw std::logic_error("malformed opening");
+    out.push_back((uint8_t)o.salt.size());
+    out.insert(out.end(), o.salt.begin(), o.salt.end());
+    put_u64(out, o.path.size());
+    for (size_t i = 0; i < o.path.size(); i++) {
+        out.insert(out.end(), o.path[i].begin(), o.path[i].end());
+        out.push_back(o.position[i] ? 1 : 0);
+    }
+}
+struct Reader {
+    const uint8_t* p;
+    size_t n, o = 0;
+    const uint8_t* take(size_t k) {
+        if (o + k > n) throw std::runtime_error("truncated proof");
+        const uint8_t* r = p + o;
+        o += k;
+        return r;
+    }
+    uint64_t u64() {
+        const uint8_t* b = take(8);
+        uint64_t v = 0;
+        for (int i = 0; i < 8; i++) v |= (uint64_t)b[i] << (8 * i);
+        return v;
+    }
+    std::array<uint8_t, 32> digest() {
+        std::array<uint8_t, 32> d;
+        const uint8_t* b = take(32);
+        for (int i = 0; i < 32; i++) d[i] = b[i];
+        return d;
+    }
+    MerkleOpening opening() {
+        MerkleOpening m;
+        m.index = u64();
+        m.value = BabyBear{u64()};
+        size_t sl = *take(1);
+        const uint8_t* sp = take(sl);
+        m.salt.assign(sp, sp + sl);
+        uint64_t len = u64();
+        if (len > 64) throw std::runtime_error("implausible path length");
+        for (uint64_t i = 0; i < len; i++) {
+            m.path.push_back(digest());
+            m.position.push_back(*take(1) != 0);
+        }
+        return m;
+    }
+};
+}  // namespace detail
+
+inline std::vector<uint8_t> serialize_proof(const StarkProof& p) {
+    std::vector<uint8_t> out;
+    detail::put_u64(out, p.trace_len);
+    detail::put_u64(out, p.lde_size);
+    out.insert(out.end(), p.trace_commitment.begin(), p.trace_commitment.end());
+    out.insert(out.end(), p.quotient_commitment.begin(), p.quotient_commitment.end());
+    for (BabyBear v : {p.t_z, p.t_gz, p.t_ggz, p.q_z}) detail::put_u64(out, v.value);
+    detail::put_u64(out, p.fri_commitments.size());
+    for (const auto& r : p.fri_commitments) out.insert(out.end(), r.begin(), r.end());
+    detail::put_u64(out, p.fri_final_layer.size());
+    for (BabyBear v : p.fri_final_layer) detail::put_u64(out, v.value);
+    detail::put_u64(out, p.query_proofs.size());
+    for (const QueryProof& q : p.query_proofs) {
+        detail::put_u64(out, q.index);
+        for (const MerkleOpening* o : {&q.deep_opening, &q.deep_opening_pair, &q.trace_opening, &q.trace_opening_g, &q.trace_opening_gg,
+                                       &q.quotient_opening})
+            detail::put_opening(out, *o);
+        detail::put_u64(out, q.fri_openings.size());
+        for (const auto& pr : q.fri_openings) {
+            detail::put_opening(out, pr.first);
+            detail::put_opening(out, pr.second);
+        }
+    }
+    return out;
+}
+
+inline StarkProof deserialize_proof(const uint8_t* data, size_t len) {
+    detail::Reader r{data, len};
+    StarkProof p;
+    p.trace_len = r.u64();
+    p.lde_size = r.u64();
+    p.trace_commitment = r.digest();
+    p.quotient_commitment = r.digest();
+    p.t_z = BabyBear{r.u64()};
+    p.t_gz = BabyBear{r.u64()};
+    p.t_ggz = BabyBear{r.u64()};
+    p.q_z = BabyBear{r.u64()};
+    for (uint64_t i = 0, n = r.u64(); i < n; i++) p.fri_commitments.push_back(r.digest());
+    for (uint64_t i = 0, n = r.u64(); i < n; i++) p.fri_final_layer.push_back(BabyBear{r.u64()});
+    for (uint64_t i = 0, n = r.u64(); i < n; i++) {
+        QueryProof q;
+        q.index = r.u64();
+        for (MerkleOpening* o : {&q.deep_opening, &q.deep_opening_pair, &q.trace_opening, &q.trace_opening_g, &q.trace_opening_gg, &q.quotient_opening})
+            *o = r.opening();
+        for (uint64_t j = 0, m = r.u64(); j < m; j++) {
+            MerkleOpening a = r.opening();
+            MerkleOpening b = r.opening();
+            q.fri_openings.emplace_back(std::move(a), std::move(b));
+        }
+        p.query_proofs.push_back(std::move(q));
+    }
+    if (r.o != len) throw std::runtime_error("trailing bytes after the proof");
+    return p;
+}
 
 }  // namespace toyni
