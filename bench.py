@@ -589,6 +589,30 @@ def run_ours(args, rank, world, local_rank):
         th.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the same pipeline through the u32 host entry point (bb_ntt_host_u32: NOT the reference's u64 signature, reported
+    # beside the drop-in number): 4 B/element each way
+    hosts32 = [torch.empty(n, dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(NTHR)]
+    for h in hosts32:
+        h[:] = hv.astype(np.uint32)
+
+    def pump32(k, count):
+        torch.cuda.set_device(local_rank)
+        for _ in range(count):
+            rc = L.bb_ntt_host_u32(ctypes.c_void_p(ctxs[k]), hosts32[k].ctypes.data, 0)
+            errs[k] = errs[k] or rc
+
+    for k in range(NTHR):
+        pump32(k, 1)
+    barrier()
+    threads = [threading.Thread(target=pump32, args=(k, e2e_steps // NTHR)) for k in range(NTHR)]
+    t0 = time.perf_counter()
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    torch.cuda.synchronize()
+    e2e_u32_s = c.max_over_ranks([time.perf_counter() - t0])[0]
+    del hosts32
     e2e_err = max(errs)  # never raise here: the other ranks would wait in the reduction below forever
     for cx in ctxs:
         L.ntt_ctx_destroy(ctypes.c_void_p(cx))
@@ -630,6 +654,9 @@ def run_ours(args, rank, world, local_rank):
                 "steps": e2e_steps, "api": f"ntt_run_inplace (src/ntt.rs:108) on pinned host u64, {NTHR} host threads with "
                                            "one context each (H2D of one overlaps D2H and kernels of the others)",
                 "serial_value": e2e_serial_val, "serial_api": "one caller, one context: ntt_cuda as in src/ntt.rs:224-236",
+                "u32_host_value": world * n * e2e_steps / e2e_u32_s / 1e9,
+                "u32_host_api": "bb_ntt_host_u32: the same pipeline on canonical u32 host values (4 B/element each way); not the "
+                                "reference's signature (src/ntt.rs stores u64), reported beside the drop-in number, not instead of it",
                 "pcie_peak_gbs": pcie, "pcie_frac": per_gpu_bytes_s / 1e9 / min(pcie.values()),
                 "pcie_note": "bytes per direction per GPU / time / the slower of the two measured one-way pinned-copy rates "
                              "(max over ranks); PCIe moves 16 B per element here against 8 B of algorithmic HBM traffic"},

@@ -53,6 +53,9 @@ void intt_run_inplace(void* ctx, uint64_t* h_data);
  * reference's void signatures cannot report a failed copy or launch (cuda/ntt_kernel.cu:249-292 ignores them). */
 int ntt_run_inplace_rc(void* ctx, uint64_t* h_data);
 int intt_run_inplace_rc(void* ctx, uint64_t* h_data);
+/* Not part of the drop-in surface (src/ntt.rs keeps a BabyBear in a u64): the same in-place host transform on canonical
+ * u32 values, i.e. half the PCIe bytes.  dir: 0 forward, 1 inverse. */
+int bb_ntt_host_u32(void* ctx, uint32_t* h_data, int dir);
 
 /* ------------------------------------------------------------------------------------------
  * 2. Device-resident, stream-ordered API.
@@ -106,6 +109,10 @@ int bb_peer_wait_device(void* d_flags, uint32_t nranks, uint32_t epoch, void* d_
 int bb_ipc_get_handle(const void* d_ptr, uint8_t handle_out[64]);
 int bb_ipc_open_handle(const uint8_t handle[64], void** d_ptr_out);
 int bb_ipc_close_handle(void* d_ptr);
+
+/* BabyBearDomain::elements (src/math/domain.rs:61-69): d_out[i] = shift * w^i, i < 2^log_n; shift = 1 is
+ * roots_of_unity_domain (src/ntt.rs:69-81).  From the twiddle cache, no sequential running product. */
+int bb_domain_elements_device(uint32_t log_n, uint32_t shift, uint32_t* d_out);
 
 /* BabyBearDomain::fft on a coset (src/math/domain.rs:107-123,154-162): zero-pad/truncate the
  * n_coeffs coefficients to 2^log_size, multiply by shift^i, forward NTT.  Fused into the first
@@ -205,6 +212,9 @@ void bb_release(void);                                  /* free all cached devic
 /* BabyBearDomain::fft / ifft (src/math/domain.rs:107-123, :85-102) */
 int toyni_domain_fft(const uint64_t* coeffs, size_t n_coeffs, size_t size, uint64_t shift, uint64_t* evals_out);
 int toyni_domain_ifft(const uint64_t* evals, size_t size, uint64_t shift, uint64_t* coeffs_out);
+/* roots_of_unity_domain(n) (src/ntt.rs:69-81) and BabyBearDomain::elements() (src/math/domain.rs:61-69) */
+int toyni_roots_of_unity_domain(size_t n, uint64_t* out);
+int toyni_domain_elements(size_t size, uint64_t shift, uint64_t* out);
 /* fft_ext / ifft_ext (src/math/domain.rs:129-137): AoS Ext arrays, 4 x u64 per element */
 int toyni_domain_fft_ext(const uint64_t* coeffs, size_t n_coeffs, size_t size, uint64_t shift, uint64_t* evals_out);
 int toyni_domain_ifft_ext(const uint64_t* evals, size_t size, uint64_t shift, uint64_t* coeffs_out);

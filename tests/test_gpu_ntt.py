@@ -344,3 +344,29 @@ def test_two_contexts_on_two_threads_do_not_share_scratch():
     for t in ts:
         t.join()
     assert results == {18: True, 19: True}
+
+
+def test_roots_of_unity_domain_and_u32_host_entry(D):
+    """a6: roots_of_unity_domain (src/ntt.rs:69-81, its test :360-379: 16 distinct roots, w^16 = 1) from the device twiddle
+    cache; the device-resident domain elements; and the u32 host entry point (half the PCIe bytes of the u64 drop-in)."""
+    import ctypes
+    import torch
+    from toyni_b200 import ntt
+    from toyni_b200.lib import lib
+    dom = ntt.roots_of_unity_domain(16)
+    assert len(set(int(v) for v in dom)) == 16 and dom[0] == 1
+    assert pow(int(dom[1]), 16, P) == 1
+    for log_n in (0, 1, 9, 20):
+        assert np.array_equal(ntt.roots_of_unity_domain(1 << log_n), O.roots_of_unity_domain(1 << log_n))
+    d = torch.empty(1 << 18, dtype=torch.int32, device="cuda")
+    assert lib().bb_domain_elements_device(18, 7, ctypes.c_void_p(d.data_ptr())) == 0
+    assert np.array_equal(D.to_host(d), O.domain_elements(1 << 18, 7))
+    L = lib()
+    x = O.random_field(1 << 20, seed=5)
+    ctx = L.ntt_ctx_create(1 << 20)
+    v = x.astype(np.uint32)
+    assert L.bb_ntt_host_u32(ctypes.c_void_p(ctx), v.ctypes.data, 0) == 0
+    assert np.array_equal(v.astype(np.uint64), O.ntt(x, threads=4))
+    assert L.bb_ntt_host_u32(ctypes.c_void_p(ctx), v.ctypes.data, 1) == 0
+    assert np.array_equal(v.astype(np.uint64), x)
+    L.ntt_ctx_destroy(ctypes.c_void_p(ctx))

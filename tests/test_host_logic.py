@@ -229,3 +229,19 @@ def test_pass_planner_without_a_device():
         assert 1 <= npass <= 3 and sum(rows[i] for i in range(npass)) == log_n
         if log_n in want:
             assert [rows[i] for i in range(npass)] == want[log_n]
+
+
+def test_tma_kernel_index_model_is_a_dft():
+    """tools/v7_model.py restates which shared-memory row, twiddle-table entry and inter-pass factor every lane of the
+    TMA-staged two-pass kernel (ntt_pass_v7.cuh) uses, with the radix as a parameter; at radix 4 (n = 2^12) the model must
+    be the DFT of src/ntt.rs:24-53 and its inverse, which pins the chunk layout, the swizzle and the A * beta split."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("v7_model", os.path.join(ROOT, "tools", "v7_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    g, n = 2, 4096
+    x = O.random_field(n, seed=77)
+    got = np.array([int(v) for v in m.two_pass_ntt([int(v) for v in x], g)], dtype=np.uint64)
+    assert np.array_equal(got, O.ntt(x))
+    back = np.array([int(v) for v in m.two_pass_ntt([int(v) for v in got], g, inverse=True)], dtype=np.uint64)
+    assert np.array_equal(back, x)

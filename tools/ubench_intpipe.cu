@@ -3,6 +3,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench_intpipe ubench_intpipe.cu
 #include <cstdio>
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #define P 2013265921u
 #define ITERS 4096
@@ -67,9 +68,10 @@ __global__ void __launch_bounds__(256) kern(uint32_t* out, uint32_t seed, uint32
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+static int g_ctas_per_sm = 8;  // 8 CTAs x 8 warps = 16 warps per scheduler; argv[1] overrides (2 = 4 warps per scheduler)
 template <int OP>
 void run(const char* name, double ops_per_iter, int sms, double mhz) {
-    uint32_t* out; int blocks = sms * 8, threads = 256;
+    uint32_t* out; int blocks = sms * g_ctas_per_sm, threads = 256;
     cudaMalloc(&out, (size_t)blocks * threads * 4);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int r = 0; r < 3; r++) kern<OP><<<blocks, threads>>>(out, 12345u, 1234567u, 2633989657u);
@@ -85,11 +87,12 @@ void run(const char* name, double ops_per_iter, int sms, double mhz) {
     cudaFree(out);
 }
 
-int main() {
+int main(int argc, char** argv) {
+    if (argc > 1) g_ctas_per_sm = atoi(argv[1]);
     cudaDeviceProp pr; cudaGetDeviceProperties(&pr, 0);
     int sms = pr.multiProcessorCount; int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
     double mhz = khz / 1000.0;
-    printf("%s SMs=%d clock=%.0f MHz L2=%d MB smem/SM=%zu\n", pr.name, sms, mhz, pr.l2CacheSize >> 20, pr.sharedMemPerMultiprocessor);
+    printf("%s SMs=%d clock=%.0f MHz L2=%d MB smem/SM=%zu, %d warps per scheduler\n", pr.name, sms, mhz, pr.l2CacheSize >> 20, pr.sharedMemPerMultiprocessor, g_ctas_per_sm * 2);
     run<0>("IMAD", 1, sms, mhz);
     run<1>("IMAD.HI.U32", 1, sms, mhz);
     run<2>("IMAD.WIDE.U32", 1, sms, mhz);

@@ -25,5 +25,5 @@ e1.record()
 torch.cuda.synchronize()
 w = (C.c_uint32 * 16)()
 L.bb_ntt_diag(w)
-print("cols", os.environ.get("TOYNI_V7_COLS"), "flags", os.environ.get("TOYNI_V7_FLAGS"), "promo", os.environ.get("TOYNI_V7_L2PROMO"), "pdl", os.environ.get("TOYNI_NTT_PDL"),
+print("flags", os.environ.get("TOYNI_V7_FLAGS"), "promo", os.environ.get("TOYNI_V7_L2PROMO"), "pdl", os.environ.get("TOYNI_NTT_PDL"),
       round(e0.elapsed_time(e1) * 1000 / reps, 2), "us per transform; diag", list(w)[:9], flush=True)

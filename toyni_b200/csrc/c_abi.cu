@@ -165,6 +165,29 @@ void intt_run_inplace(void* ctx, uint64_t* h_data) { run_host_inplace((NttCtx*)c
 int ntt_run_inplace_rc(void* ctx, uint64_t* h_data) { return run_host_inplace((NttCtx*)ctx, h_data, false); }
 int intt_run_inplace_rc(void* ctx, uint64_t* h_data) { return run_host_inplace((NttCtx*)ctx, h_data, true); }
 
+// The same host-pointer transform on u32 values (4 bytes per element over PCIe instead of the reference's 8): NOT part of
+// the drop-in surface — src/ntt.rs stores a BabyBear as u64 — but what a host that already keeps canonical u32 should call.
+int bb_ntt_host_u32(void* ctx, uint32_t* h_data, int dir) {
+    NttCtx* c = (NttCtx*)ctx;
+    if (!c || !h_data || (dir != 0 && dir != 1)) return note((int)cudaErrorInvalidValue);
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t n = c->n;
+    cudaStream_t s = c->stream;
+    CK(cudaMemcpyAsync(c->d32, h_data, n * 4, cudaMemcpyHostToDevice, s));
+    NttDesc d{};
+    d.log_n = (int)c->log_n;
+    d.inverse = dir == 1;
+    d.in = c->d32;
+    d.out = c->d32;
+    d.n_in = n;
+    d.batch = 1;
+    d.batch_stride_in = d.batch_stride_out = n;
+    CK(ntt_execute(d, s));
+    g_launches += (unsigned)ntt_plan_for((int)c->log_n, 0, 1).npass;
+    CK(cudaMemcpyAsync(h_data, c->d32, n * 4, cudaMemcpyDeviceToHost, s));
+    return note((int)cudaStreamSynchronize(s));
+}
+
 // ================================================================== 2. device-resident API
 int bb_last_error(void) { return g_last_error; }
 const char* bb_last_error_string(void) { return cudaGetErrorString((cudaError_t)g_last_error); }
@@ -636,6 +659,30 @@ int bb_warmup(uint32_t log_n) {
     return note(engine_warmup((int)log_n, cur_stream()));
 }
 void bb_release(void) { engine_release(); }
+
+}  // extern "C"
+
+// out[i] = shift * w^i for i < 2^log_n, w = get_root_of_unity(log_n): BabyBearDomain::elements (src/math/domain.rs:61-69);
+// shift = 1 gives roots_of_unity_domain (src/ntt.rs:69-81).  The reference builds both with n sequential multiplications.
+template <typename T>
+__global__ void __launch_bounds__(256) domain_elements_kernel(PowTable tab, uint32_t shift_m, T* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (T)monty_mul(pow_plain(tab, (uint32_t)i), shift_m);
+}
+
+extern "C" {
+
+int bb_domain_elements_device(uint32_t log_n, uint32_t shift, uint32_t* d_out) {
+    if (log_n > (uint32_t)MAX_LOG_N || shift == 0 || shift >= P || !d_out) return note((int)cudaErrorInvalidValue);
+    if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
+    PowTable tab;
+    CK(engine_pow_table(root_of_unity(log_n), (int)log_n, 1u, &tab));
+    const size_t n = (size_t)1 << log_n;
+    domain_elements_kernel<uint32_t><<<conv_blocks(n), 256, 0, cur_stream()>>>(tab, to_monty(shift), d_out, n);
+    g_launches++;
+    return note((int)cudaGetLastError());
+}
 int bb_ntt_diag(uint32_t words_out[16]) { return note(engine_diag_words(words_out)); }
 
 }  // extern "C"
@@ -772,5 +819,23 @@ int toyni_merkle_commit(const uint64_t* values, size_t n, int limbs, const uint8
     if (nodes_out) CK(cudaMemcpyAsync(nodes_out, cur_stage().nodes, count * 32, cudaMemcpyDeviceToHost, s));
     return note((int)cudaStreamSynchronize(s));
 }
+
+/* roots_of_unity_domain (src/ntt.rs:69-81) / BabyBearDomain::elements (src/math/domain.rs:61-69): size values, u64 */
+int toyni_domain_elements(size_t size, uint64_t shift, uint64_t* out) {
+    if (!is_pow2(size) || log2_of(size) > (uint32_t)MAX_LOG_N || shift == 0 || !out) return note((int)cudaErrorInvalidValue);
+    if (!bb_device_ok()) return note((int)cudaErrorNoKernelImageForDevice);
+    std::lock_guard<std::mutex> lk(cur_stage().mu);
+    cudaStream_t s = cur_stream();
+    CK(grow(&cur_stage().d64, &cur_stage().n64, size));
+    PowTable tab;
+    const uint32_t log_n = log2_of(size);
+    CK(engine_pow_table(root_of_unity(log_n), (int)log_n, 1u, &tab));
+    domain_elements_kernel<uint64_t><<<conv_blocks(size), 256, 0, s>>>(tab, to_monty((uint32_t)(shift % P)), cur_stage().d64, size);
+    g_launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, cur_stage().d64, size * 8, cudaMemcpyDeviceToHost, s));
+    return note((int)cudaStreamSynchronize(s));
+}
+int toyni_roots_of_unity_domain(size_t n, uint64_t* out) { return toyni_domain_elements(n, 1, out); }
 
 }  // extern "C"

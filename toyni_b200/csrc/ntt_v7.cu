@@ -71,6 +71,11 @@ static int map_get(const uint32_t* in, size_t ncols, size_t batch, size_t stride
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(key);
     if (it == cache.end()) {
+        if (cache.size() >= 4096) {  // a process that walks through thousands of distinct buffers: start over (entries are 128 B each)
+            cudaDeviceSynchronize();
+            for (auto& kv : cache) cudaFree(kv.second);
+            cache.clear();
+        }
         alignas(64) CUtensorMap m;
         int rc = make_map(in, ncols, batch, stride, cols, box_d2, &m);
         if (rc) return rc;
@@ -120,10 +125,11 @@ static int launch_one(const CUtensorMap* map, const CUtensorMap* omap, V7Params 
 }
 
 int launch_pass_v7(bool pass2, const uint32_t* in, size_t ncols, size_t batch, size_t in_batch_stride, V7Params p, bool pdl, cudaStream_t s) {
-    static int cols = -1, flags = -1;
-    if (cols < 0) {
-        const char* e = getenv("TOYNI_V7_COLS");
-        cols = (e && atoi(e) == 4) ? 4 : 8;
+    // 8 columns (32-byte rows, one CTA of 16 warps per SM).  The kernel template also builds with 4 columns (two CTAs of
+    // 8 warps per SM); that shape measured 152 us against 116 us — rows below a 32-byte sector — and is not instantiated.
+    constexpr int cols = 8;
+    static int flags = -1;
+    if (flags < 0) {
         const char* f = getenv("TOYNI_V7_FLAGS");
         flags = f ? atoi(f) : 0;
     }
@@ -142,7 +148,6 @@ int launch_pass_v7(bool pass2, const uint32_t* in, size_t ncols, size_t batch, s
         rc = map_get(p.out, ncols, batch, (size_t)p.out_batch_stride, cols, 8, &omap);
         if (rc) return rc;
     }
-    if (cols == 4) return pass2 ? launch_one<true, 4>(map, omap, p, ncols, batch, pdl, s) : launch_one<false, 4>(map, omap, p, ncols, batch, pdl, s);
     return pass2 ? launch_one<true, 8>(map, omap, p, ncols, batch, pdl, s) : launch_one<false, 8>(map, omap, p, ncols, batch, pdl, s);
 }
 

@@ -52,9 +52,10 @@ class BabyBearDomain:
 
     def elements(self):
         """{shift * omega^i} (:61-69) = the coset evaluation of the polynomial X."""
-        if self.size == 1:
-            return np.array([self.shift], dtype=np.uint64)
-        return self.fft(np.array([0, 1], dtype=np.uint64))
+        self._require_gpu()
+        out = np.empty(self.size, dtype=np.uint64)
+        check(lib().toyni_domain_elements(self.size, int(self.shift) % P, out.ctypes.data), "toyni_domain_elements")
+        return out
 
     def fft(self, coeffs):
         """:107-123: zero-pad / truncate to `size`, coset shift, forward NTT."""

@@ -25,6 +25,10 @@ _SIGNATURES = {
     "intt_run_inplace": ([C.c_void_p, C.c_void_p], None),
     "ntt_run_inplace_rc": ([C.c_void_p, C.c_void_p], C.c_int),
     "intt_run_inplace_rc": ([C.c_void_p, C.c_void_p], C.c_int),
+    "bb_ntt_host_u32": ([C.c_void_p, C.c_void_p, C.c_int], C.c_int),
+    "bb_domain_elements_device": ([C.c_uint32, C.c_uint32, C.c_void_p], C.c_int),
+    "toyni_roots_of_unity_domain": ([C.c_size_t, C.c_void_p], C.c_int),
+    "toyni_domain_elements": ([C.c_size_t, C.c_uint64, C.c_void_p], C.c_int),
     # 2. device-resident API
     "bb_last_error": ([], C.c_int),
     "bb_last_error_string": ([], C.c_char_p),

@@ -88,3 +88,15 @@ def ntt_cuda(values):
 def intt_cuda(values):
     """Inverse NTT on the GPU, in place (src/ntt.rs:239-251)."""
     _run(values, True)
+
+
+def roots_of_unity_domain(n):
+    """[omega^i for i < n] (src/ntt.rs:69-81), from the device twiddle cache instead of n sequential multiplications."""
+    if not cuda_available():
+        raise ToyniCudaError("CUDA not available")
+    assert n > 0 and (n & (n - 1)) == 0, "Domain size must be power of 2"  # :70
+    out = np.empty(n, dtype=np.uint64)
+    err = lib().toyni_roots_of_unity_domain(n, out.ctypes.data)
+    if err:
+        raise ToyniCudaError("CUDA roots_of_unity_domain failed: " + lib().cuda_get_error_string(err).decode())
+    return out
