@@ -13,8 +13,8 @@ The rest of the metric rides on the same JSON line:
             64 x 2^22 column-sharded NTTs, the 2^25 Ext fold chain on cyclic shards and the sharded FRI commit loop
             (BASELINE configs[3], [4]); every record carries `parity_ok` = outputs of ALL ranks compared with the CPU
             oracle (checker only, outside the timed regions).
-  `extras`  (N = 1)   — coset LDE 2^20 -> 2^25, salted Merkle commit of 2^25 leaves, FRI commit loop (configs[2], [3]),
-            each with its own roofline.
+  `extras`  (N = 1)   — coset LDE 2^20 -> 2^25 and the salted Merkle commit of its 2^25 leaves (configs[2]), each with
+            its own roofline (the FRI commit loop of configs[3] is `sharded.fri_commit_ext_2^25`).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-sharded] [--no-extras]
 """
@@ -386,7 +386,6 @@ def sharded_fri_commit(c, steps):
         return challenge
     local0 = full[c.rank::c.world].contiguous()
     roots, layers, nodes, tail = MG.fri_commit_sharded(local0, log_m, shift, final, salts_for, make_challenge(), c.rank, c.world, B)
-    final_layer = tail[-1]
     parity = None
     if c.rank == 0:  # checker: the oracle's commit loop on the same codeword, salts and transcript
         from oracle import oracle as O
@@ -409,8 +408,7 @@ def sharded_fri_commit(c, steps):
             "ms": ms, "ms_median": statistics.median(times) * 1e3, "layers": len(roots), "scaling": "strong", "steps": steps,
             "leaves_hashed": leaves, "g_sha256_compressions_s": comps / (ms * 1e-3) / 1e9,
             "timing": "host wall clock around the loop (it synchronises once per layer for the transcript), best of steps, max over ranks",
-            "parity_ok": parity, "parity": "all layer roots against the CPU oracle's commit loop (same salts, same transcript)",
-            "final_layer_constant": bool((final_layer == final_layer[0]).all().item()) if final_layer.numel() else None}
+            "parity_ok": parity, "parity": "all layer roots against the CPU oracle's commit loop (same salts, same transcript)"}
 
 
 def run_sharded(c, args):
