@@ -72,6 +72,7 @@ int bb_dev_alloc(void** d_ptr, size_t bytes);
 int bb_dev_free(void* d_ptr);
 int bb_h2d(void* d_dst, const void* h_src, size_t bytes);            /* async on the stream */
 int bb_d2h(void* h_dst, const void* d_src, size_t bytes);            /* async on the stream */
+int bb_d2d(void* d_dst, const void* d_src, size_t bytes);            /* async on the stream */
 /* width conversion between the reference's u64 storage and device u32 (values are reduced mod p) */
 int bb_narrow_u64_to_u32(const uint64_t* d_src, uint32_t* d_dst, size_t count);
 int bb_widen_u32_to_u64(const uint32_t* d_src, uint64_t* d_dst, size_t count);

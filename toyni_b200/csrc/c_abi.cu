@@ -224,6 +224,9 @@ int bb_h2d(void* d_dst, const void* h_src, size_t bytes) {
 int bb_d2h(void* h_dst, const void* d_src, size_t bytes) {
     return note((int)cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, cur_stream()));
 }
+int bb_d2d(void* d_dst, const void* d_src, size_t bytes) {
+    return note((int)cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, cur_stream()));
+}
 int bb_narrow_u64_to_u32(const uint64_t* d_src, uint32_t* d_dst, size_t count) {
     if (count == 0) return 0;
     narrow_kernel<<<conv_blocks(count), 256, 0, cur_stream()>>>(d_src, d_dst, count);

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "bb_dev_free": ([C.c_void_p], C.c_int),
     "bb_h2d": ([C.c_void_p, C.c_void_p, C.c_size_t], C.c_int),
     "bb_d2h": ([C.c_void_p, C.c_void_p, C.c_size_t], C.c_int),
+    "bb_d2d": ([C.c_void_p, C.c_void_p, C.c_size_t], C.c_int),
     "bb_narrow_u64_to_u32": ([C.c_void_p, C.c_void_p, C.c_size_t], C.c_int),
     "bb_widen_u32_to_u64": ([C.c_void_p, C.c_void_p, C.c_size_t], C.c_int),
     "bb_ntt_device": ([C.c_void_p, C.c_uint32, C.c_int], C.c_int),
