@@ -135,6 +135,13 @@ int bb_fri_fold_device(const uint32_t* d_evals, size_t m, uint32_t x0, const uin
  * rank, rank+nranks, ...; m_local = m/nranks values in, m_local/2 out, no communication. */
 int bb_fri_fold_shard_device(const uint32_t* d_evals, size_t m_local, uint32_t log_m, uint32_t x0,
                              const uint32_t beta[4], int limbs, uint32_t nranks, uint32_t rank, uint32_t* d_out);
+/* A whole fold chain on one cyclic shard in ONE call (the prover's loop, src/fibonacci.rs:213-231, without the commits):
+ * layer k+1 = fold(layer k) with beta = betas[k * limbs ..], x0 squared from layer to layer, while the layer has more
+ * than `until` values and at least 2 * nranks.  The folded layers land back to back in d_layers
+ * (m_local/2 + m_local/4 + ... values); *folds_out = number of folds.  No host work between the launches. */
+int bb_fri_fold_chain_shard_device(const uint32_t* d_layer0, size_t m_local, uint32_t log_m, uint32_t shift, const uint32_t* betas,
+                                   size_t nbetas, int limbs, uint32_t nranks, uint32_t rank, size_t until, uint32_t* d_layers,
+                                   size_t* folds_out);
 /* Reference signature with an explicit xs array (only xs[0..m/2) is read, src/math/fri.rs:13-16). */
 int bb_fri_fold_xs_device(const uint32_t* d_evals, size_t m, const uint32_t* d_xs, const uint32_t beta[4], int limbs,
                           uint32_t* d_out);

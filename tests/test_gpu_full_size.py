@@ -152,3 +152,32 @@ def test_columns_64_x_2_22(D):
         assert np.array_equal(D.to_host(got[i]), O.ntt(x[i], threads=CORES))
     assert torch.equal(D.ntt_batch_(got, True), dx)
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("n_coeffs,shift", [((1 << 20) + 140, 7), (12345, 7), (1 << 21, 7), (1 << 20, 1), ((1 << 21) - 4097, 3)])
+def test_lde_to_2_25_ragged_inputs(D, oracle_threads, n_coeffs, shift):
+    """The blowup-32 plan (expansion pass + TMA-staged pass 2) on the inputs it must cope with: the masked trace polynomial
+    of a 2^20-row proof (2^20 + 140 coefficients, src/fibonacci.rs:117-121), short and ragged coefficient vectors, twice the
+    trace length, and the unshifted domain (src/math/domain.rs:107-123): every evaluation against the oracle."""
+    import torch
+    c = O.random_field(n_coeffs, seed=330 + n_coeffs % 97)
+    ref = O.domain_fft(c, 1 << 25, shift)
+    ev = D.coset_fft(D.to_device(c), 1 << 25, shift)
+    assert np.array_equal(D.to_host(ev), ref)
+    del ev
+    torch.cuda.empty_cache()
+
+
+def test_lde_to_2_25_matches_the_tile_kernel_plan(D):
+    """Same LDE through the general three-pass plan (bb_ntt_set_kernel(0)): identical bits."""
+    import torch
+    from toyni_b200.lib import lib
+    c = D.to_device(O.random_field((1 << 20) + 140, seed=77))
+    a = D.coset_fft(c, 1 << 25, 7)
+    lib().bb_ntt_set_kernel(0)
+    try:
+        b = D.coset_fft(c, 1 << 25, 7)
+    finally:
+        lib().bb_ntt_set_kernel(1)
+    assert torch.equal(a, b)
+    torch.cuda.empty_cache()

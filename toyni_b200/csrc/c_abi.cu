@@ -401,6 +401,30 @@ int bb_fri_fold_shard_device(const uint32_t* d_evals, size_t m_local, uint32_t l
     g_launches++;
     return 0;
 }
+int bb_fri_fold_chain_shard_device(const uint32_t* d_layer0, size_t m_local, uint32_t log_m, uint32_t shift, const uint32_t* betas,
+                                   size_t nbetas, int limbs, uint32_t nranks, uint32_t rank, size_t until, uint32_t* d_layers,
+                                   size_t* folds_out) {
+    if ((limbs != 1 && limbs != 4) || nranks == 0 || rank >= nranks || m_local * nranks != ((size_t)1 << log_m) || !betas)
+        return note((int)cudaErrorInvalidValue);
+    size_t m = (size_t)1 << log_m, folds = 0;
+    uint32_t x0 = shift % P;
+    const uint32_t* src = d_layer0;
+    uint32_t* dst = d_layers;
+    cudaStream_t s = cur_stream();
+    while (m > until && m / 2 >= nranks) {
+        if (folds >= nbetas) return note((int)cudaErrorInvalidValue);
+        const size_t ml = m / nranks;
+        CK(fri_fold_coset(src, dst, ml, limbs, (int)log_m - (int)folds, x0, betas + folds * limbs, nranks, rank, s));
+        g_launches++;
+        src = dst;
+        dst += (ml / 2) * limbs;
+        x0 = mul(x0, x0);
+        m /= 2;
+        folds++;
+    }
+    if (folds_out) *folds_out = folds;
+    return 0;
+}
 int bb_fri_fold_xs_device(const uint32_t* d_evals, size_t m, const uint32_t* d_xs, const uint32_t beta[4], int limbs,
                           uint32_t* d_out) {
     if (limbs != 1 && limbs != 4) return note((int)cudaErrorInvalidValue);

@@ -53,6 +53,7 @@ struct PowTab {
 struct DeviceState {
     uint2* tw[2] = {nullptr, nullptr};  // omega_4096^(+-i), i < 2048
     uint2 tw16[2][8];
+    uint2* tw8192 = nullptr;            // omega_8192^i, i < 4096 (forward): the LDE expansion pass, built on first use
     std::map<std::tuple<uint32_t, int, uint32_t>, PowTab> pow_tabs;  // (g, log_total, scale) -> tables
     // one scratch buffer per stream: transforms on different streams (e.g. two legacy contexts used from two host
     // threads) may execute concurrently and must not share the intermediate array
@@ -177,6 +178,8 @@ void engine_release() {
     cudaDeviceSynchronize();
     DeviceState& st = it->second;
     for (int i = 0; i < 2; i++) cudaFree(st.tw[i]);
+    cudaFree(st.tw8192);
+    st.tw8192 = nullptr;
     for (auto& kv : st.pow_tabs) {
         cudaFree(kv.second.lo);
         cudaFree(kv.second.hi);
@@ -332,6 +335,62 @@ static int v7_launch(const NttDesc& d, V7Job& job, cudaStream_t stream) {
     return launch_pass_v7(true, job.scratch, (size_t)V7_R, d.batch, n, p, job.pdl, stream);
 }
 
+// Blowup-32 LDE 2^20 -> 2^25 (zero-padded forward transform of at most 2^21 coefficients, optional coset shift):
+// the expansion pass (lde_expand.cuh: 32 coset transforms of 256 points per column) and pass 2 of the TMA-staged kernel
+// on 8192 columns.  13 + 12 = 25 butterfly stages shrink to 8 + 12 and the data cross HBM twice instead of three times.
+struct LdeJob {
+    LdeParams lp;
+    V7Params p;
+    uint32_t* scratch;
+};
+static bool lde25_applies(const NttDesc& d) {
+    return d.log_n == LDE::LOG_ROWS + LDE::LOG_COLS && !d.inverse && d.log_inner == 0 && d.batch == 1 && !d.scatter && d.n_in > 0 &&
+           d.n_in <= ((size_t)1 << 21) && v7_enabled() && g_plan_override.find(d.log_n) == g_plan_override.end() &&
+           ((((uintptr_t)d.in | (uintptr_t)d.out) & 15u) == 0);
+}
+static int lde25_prepare(DeviceState& st, const NttDesc& d, cudaStream_t stream, LdeJob* job) {
+    const size_t n = (size_t)1 << d.log_n;
+    if (!st.tw8192) {
+        BB_CK(cudaMalloc(&st.tw8192, sizeof(uint2) * 4096));
+        gen_shoup_kernel<<<4096 / 256, 256>>>(st.tw8192, 4096u, to_monty(root_of_unity(LDE::LOG_ROWS)));
+        BB_CK(cudaGetLastError());
+        BB_CK(cudaDeviceSynchronize());
+    }
+    V7Params& p = job->p;
+    memset(&p, 0, sizeof p);
+    int rc = pow_table_get(st, root_of_unity(d.log_n), d.log_n, 1u, &p.tab);
+    if (rc) return rc;
+    p.tab_scaled = p.tab;
+    LdeParams& lp = job->lp;
+    memset(&lp, 0, sizeof lp);
+    lp.has_shift = d.coset_shift > 1;
+    if (lp.has_shift) {
+        rc = pow_table_get(st, d.coset_shift, d.log_n, 1u, &lp.shift);
+        if (rc) return rc;
+    }
+    rc = scratch_get(st, stream, n, &job->scratch);
+    if (rc) return rc;
+    p.tw = st.tw[0];
+    memcpy(p.tw16, st.tw16[0], sizeof p.tw16);
+    p.exp_mask = (uint32_t)(n - 1);
+    p.err = st.err_word;
+    p.out = d.out;
+    p.out_batch_stride = n;
+    p.log_pfull = LDE::LOG_ROWS;
+    lp.in = d.in;
+    lp.n_coeffs = (uint32_t)d.n_in;
+    lp.out = job->scratch;
+    lp.tw = st.tw8192;
+    return 0;
+}
+static int lde25_launch(LdeJob& job, cudaStream_t stream) {
+    const size_t n = (size_t)1 << (LDE::LOG_ROWS + LDE::LOG_COLS);
+    int rc = launch_lde_expand(job.lp, true, stream);
+    if (rc) return rc;
+    // Z[j][k1] is a row-major [4096][8192] matrix: 4096-point transforms down its 8192 columns, rows out[k2 * 8192 + k1]
+    return launch_pass_v7(true, job.scratch, (size_t)1 << LDE::LOG_ROWS, 1, n, job.p, true, stream);
+}
+
 NttPlan ntt_plan_for(int log_n, int log_inner, size_t batch) {
     std::lock_guard<std::mutex> lk(g_mu);
     return plan_locked(log_n, log_inner, batch);
@@ -392,6 +451,12 @@ int ntt_execute(const NttDesc& d, cudaStream_t stream) {
     const bool use_v7 = d.log_n == 2 * V7_LR && d.log_inner == 0 && !coset && !d.scatter && d.n_in == n && v7_enabled() &&
                         g_plan_override.find(d.log_n) == g_plan_override.end() && ((((uintptr_t)d.in | (uintptr_t)d.out) & 15u) == 0) &&
                         (d.batch == 1 || (d.batch_stride_in % 4 == 0 && d.batch_stride_out % 4 == 0));
+    if (lde25_applies(d)) {
+        LdeJob job;
+        rc = lde25_prepare(*st, d, stream, &job);
+        lk.unlock();
+        return rc ? rc : lde25_launch(job, stream);
+    }
     if (use_v7) {
         V7Job job;
         rc = v7_prepare(*st, d, stream, &job);

@@ -1,6 +1,8 @@
 // Host side of the TMA-staged two-pass transform (ntt_pass_v7.cuh): tensor maps, launch configuration.
 #include "ntt_v7.cuh"
 
+#include "lde_expand.cuh"
+
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -149,6 +151,34 @@ int launch_pass_v7(bool pass2, const uint32_t* in, size_t ncols, size_t batch, s
         if (rc) return rc;
     }
     return pass2 ? launch_one<true, 8>(map, omap, p, ncols, batch, pdl, s) : launch_one<false, 8>(map, omap, p, ncols, batch, pdl, s);
+}
+
+int launch_lde_expand(LdeParams p, bool pdl, cudaStream_t s) {
+    static int n_ctas[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (n_ctas[dev] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(lde_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LDE::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        int n_sm = 0;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        n_ctas[dev] = n_sm;  // one CTA of 16 warps and 180 KB per SM
+    }
+    p.total_tiles = 1u << (LDE::LOG_COLS - 2);
+    uint32_t ctas = (uint32_t)n_ctas[dev];
+    if (ctas > p.total_tiles) ctas = p.total_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(LDE::NT);
+    cfg.dynamicSmemBytes = LDE::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (g_pdl && pdl) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, lde_expand_kernel, p);
 }
 
 }  // namespace bb

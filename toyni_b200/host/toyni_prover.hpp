@@ -231,18 +231,32 @@ class StarkProver {
                               const std::vector<uint8_t>& salts_quot, const std::vector<uint8_t>& salts_fri) const {
         using namespace detail;
         if (!cuda_available()) throw std::runtime_error("CUDA not available");
+        const size_t lde = trace_.size() * BLOWUP;
+        if (salts_trace.size() != 16 * lde || salts_quot.size() != 16 * lde) throw std::logic_error("one 16-byte salt per LDE point");
+        DevBuf<uint8_t> d_t(salts_trace.size()), d_q(salts_quot.size()), d_f(salts_fri.size());
+        d_t.upload(salts_trace.data(), salts_trace.size());
+        d_q.upload(salts_quot.data(), salts_quot.size());
+        d_f.upload(salts_fri.data(), salts_fri.size());
+        return generate_proof_device_salts(mask, d_t.get(), d_q.get(), d_f.get(), salts_fri.size());
+    }
+
+    /// The same with the three salt arrays already on the device (16 * lde, 16 * lde and salts_fri_bytes bytes): a caller
+    /// that draws them there, or keeps them across proofs, moves nothing LDE-sized over PCIe.
+    StarkProof generate_proof_device_salts(const std::vector<BabyBear>& mask, const uint8_t* d_salts_trace, const uint8_t* d_salts_quot,
+                                           const uint8_t* d_salts_fri, size_t salts_fri_bytes) const {
+        using namespace detail;
+        if (!cuda_available()) throw std::runtime_error("CUDA not available");
         const size_t trace_len = trace_.size();
         const uint32_t log_t = log2_exact(trace_len, "trace length");
         const size_t lde = trace_len * BLOWUP;
         const uint32_t log_lde = log_t + 5;
         if (log_lde > 27) throw std::logic_error("BabyBear only supports NTT up to 2^27");
         if (mask.size() != MASK_DEGREE) throw std::logic_error("mask: MASK_DEGREE coefficients required");
-        if (salts_trace.size() != 16 * lde || salts_quot.size() != 16 * lde) throw std::logic_error("one 16-byte salt per LDE point");
         size_t bound = 1;
         while (bound < trace_len + MASK_DEGREE) bound *= 2;  // next_power_of_two of the degree bound, :201-203
         const size_t final_size = lde / bound;
         if (final_size == 0) throw std::logic_error("trace too short for the blowup");
-        if (salts_fri.size() < fri_salt_bytes(lde, final_size)) throw std::logic_error("salts_fri too short");
+        if (salts_fri_bytes < fri_salt_bytes(lde, final_size)) throw std::logic_error("salts_fri too short");
         const uint64_t g = get_root_of_unity(log_t).value;
         const uint32_t shift = (uint32_t)COSET_SHIFT;
 
@@ -266,10 +280,6 @@ class StarkProver {
         DevBuf<uint32_t> d_tpoly(n_tp);
         d_tpoly.upload(tp.data(), n_tp);
         // LDE over the shifted domain + salted commit (:124-130)
-        DevBuf<uint8_t> d_salts_t(16 * lde), d_salts_q(16 * lde), d_salts_f(salts_fri.size());
-        d_salts_t.upload(salts_trace.data(), salts_trace.size());
-        d_salts_q.upload(salts_quot.data(), salts_quot.size());
-        d_salts_f.upload(salts_fri.data(), salts_fri.size());
         DevBuf<uint32_t> d_tlde(lde);
         check(bb_coset_fft_device(d_tpoly.get(), n_tp, log_lde, shift, 1, d_tlde.get()), "bb_coset_fft_device");
         StarkProof proof;
@@ -277,7 +287,7 @@ class StarkProver {
         proof.lde_size = lde;
         const size_t nodes_lde = bb_merkle_node_count(lde);
         DevBuf<uint8_t> d_nodes_t(nodes_lde * 32), d_nodes_q(nodes_lde * 32);
-        check(bb_merkle_commit_device(d_tlde.get(), 1, lde, d_salts_t.get(), d_nodes_t.get(), proof.trace_commitment.data()), "trace commit");
+        check(bb_merkle_commit_device(d_tlde.get(), 1, lde, d_salts_trace, d_nodes_t.get(), proof.trace_commitment.data()), "trace commit");
 
         // 2. constraint and quotient (:133-153): Z_H over the coset takes BLOWUP values, 7^n (w_N^n)^i - 1
         const uint64_t b1 = pow_mod(g, trace_len - 1), b2 = pow_mod(g, trace_len - 2);
@@ -291,7 +301,7 @@ class StarkProver {
         DevBuf<uint32_t> d_qcoef(lde);
         copy_device(d_qcoef.get(), d_q.get(), lde);
         check(bb_coset_ifft_device(d_qcoef.get(), log_lde, shift, 1), "bb_coset_ifft_device");
-        check(bb_merkle_commit_device(d_q.get(), 1, lde, d_salts_q.get(), d_nodes_q.get(), proof.quotient_commitment.data()), "quotient commit");
+        check(bb_merkle_commit_device(d_q.get(), 1, lde, d_salts_quot, d_nodes_q.get(), proof.quotient_commitment.data()), "quotient commit");
 
         // 3. z outside both domains (:156-161, :378-399): z^N != 1 and (z / 7)^N != 1
         FiatShamirTranscript tr;
@@ -338,7 +348,7 @@ class StarkProver {
         DevBuf<uint8_t> d_nodes_f(node_total * 32);
         std::vector<uint8_t> roots(32 * sizes.size());
         size_t folds = 0;
-        check(bb_fri_commit_device(d_deep.get(), lde, shift, final_size, 1, d_salts_f.get(), &challenge_cb, &tr, nullptr, d_layers.get(),
+        check(bb_fri_commit_device(d_deep.get(), lde, shift, final_size, 1, d_salts_fri, &challenge_cb, &tr, nullptr, d_layers.get(),
                                    d_nodes_f.get(), roots.data(), &folds),
               "bb_fri_commit_device");
         if (folds + 1 != sizes.size()) throw std::runtime_error("unexpected number of FRI folds");
@@ -355,7 +365,7 @@ class StarkProver {
                 trees[k].n = sizes[k];
                 trees[k].vals = k == 0 ? d_deep.get() : d_layers.get() + voff;
                 trees[k].nodes = d_nodes_f.get() + noff * 32;
-                trees[k].salts = k + 1 < sizes.size() ? d_salts_f.get() + soff : nullptr;
+                trees[k].salts = k + 1 < sizes.size() ? d_salts_fri + soff : nullptr;
                 if (k) voff += sizes[k];
                 noff += bb_merkle_node_count(sizes[k]);
                 if (k + 1 < sizes.size()) soff += 16 * sizes[k];
@@ -364,8 +374,8 @@ class StarkProver {
 
         // 7. query phase (:250-295): one batched opening per tree
         const std::vector<uint64_t> queries = tr.squeeze_indices(NUM_QUERIES, lde / 2);
-        const DeviceTree trace_tree{d_tlde.get(), d_nodes_t.get(), d_salts_t.get(), lde};
-        const DeviceTree quot_tree{d_q.get(), d_nodes_q.get(), d_salts_q.get(), lde};
+        const DeviceTree trace_tree{d_tlde.get(), d_nodes_t.get(), d_salts_trace, lde};
+        const DeviceTree quot_tree{d_q.get(), d_nodes_q.get(), d_salts_quot, lde};
         std::vector<uint64_t> idx;
         for (uint64_t q : queries) {
             idx.push_back(q);

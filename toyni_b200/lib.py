@@ -60,6 +60,8 @@ _SIGNATURES = {
     "bb_fri_fold_device": ([C.c_void_p, C.c_size_t, C.c_uint32, u32p, C.c_int, C.c_void_p], C.c_int),
     "bb_fri_fold_shard_device": ([C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, u32p, C.c_int, C.c_uint32, C.c_uint32,
                                   C.c_void_p], C.c_int),
+    "bb_fri_fold_chain_shard_device": ([C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32,
+                                        C.c_uint32, C.c_size_t, C.c_void_p, C.POINTER(C.c_size_t)], C.c_int),
     "bb_fri_fold_xs_device": ([C.c_void_p, C.c_size_t, C.c_void_p, u32p, C.c_int, C.c_void_p], C.c_int),
     "bb_merkle_node_count": ([C.c_size_t], C.c_size_t),
     "bb_merkle_commit_device": ([C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),

@@ -22,6 +22,7 @@ Nothing like this exists in the reference (single device, default stream; SURVEY
 The index arithmetic is written once (`fourstep_*`) and runs either on CUDA tensors with NCCL or on CPU tensors
 with gloo, which is how the N > 1 path is tested without GPUs.
 """
+import os
 import time
 
 import numpy as np
@@ -34,6 +35,8 @@ from .lib import P
 def fourstep_split(log_n, world):
     """(n1, n2) with n1*n2 = 2^log_n, both divisible by `world`; n1 >= n2."""
     l1 = (log_n + 1) // 2
+    if os.environ.get("TOYNI_FOURSTEP_LOG_N2"):  # tuning hook (tools/nvlink_fourstep.py)
+        l1 = log_n - int(os.environ["TOYNI_FOURSTEP_LOG_N2"])
     n1, n2 = 1 << l1, 1 << (log_n - l1)
     assert n1 % world == 0 and n2 % world == 0, "transform too small for this many ranks"
     return n1, n2
@@ -243,19 +246,33 @@ class FourStepFused:
 
 def fold_chain_cuda(local, log_m, shift, betas, rank, world, until=16):
     """FRI fold chain on one cyclic shard (global indices rank, rank+G, ...), betas supplied up front.
-    Returns the list of local layers.  No communication while the layer has at least 2*world values."""
-    from .device import fri_fold_shard
+    Returns the list of local layers.  No communication while the layer has at least 2*world values.  One C call
+    (bb_fri_fold_chain_shard_device) launches every fold back to back: at eight ranks a layer lasts a few microseconds and
+    a per-layer trip through Python would be most of the chain."""
+    import ctypes as C
 
-    layers = [local]
-    x0 = shift % P
-    k = 0
-    m = 1 << log_m
+    from .device import _bind_stream, _chk
+    from .lib import check, lib
+
+    _bind_stream()
+    limbs = 4 if local.dim() == 2 else 1
+    sizes, m = [], 1 << log_m
     while m > until and (m // 2) >= world:
-        nxt = fri_fold_shard(layers[-1], log_m - k, x0, betas[k], world, rank)
-        layers.append(nxt)
-        x0 = x0 * x0 % P
         m //= 2
-        k += 1
+        sizes.append(m // world)
+    if not sizes:
+        return [local]
+    bt = np.ascontiguousarray(np.asarray([[int(v) % P for v in (b if limbs == 4 else [b])] for b in betas[:len(sizes)]],
+                                         dtype=np.uint32).reshape(-1))
+    flat = torch.empty((sum(sizes), 4) if limbs == 4 else (sum(sizes),), dtype=torch.int32, device=local.device)
+    folds = C.c_size_t(0)
+    check(lib().bb_fri_fold_chain_shard_device(_chk(local), local.shape[0], log_m, shift % P, bt.ctypes.data, len(sizes), limbs, world, rank,
+                                               until, _chk(flat), C.byref(folds)), "bb_fri_fold_chain_shard_device")
+    assert folds.value == len(sizes)
+    layers, off = [local], 0
+    for s in sizes:
+        layers.append(flat[off:off + s])
+        off += s
     return layers
 
 
