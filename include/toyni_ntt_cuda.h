@@ -70,6 +70,11 @@ int bb_sync(void);                       /* synchronise that stream */
 
 int bb_dev_alloc(void** d_ptr, size_t bytes);
 int bb_dev_free(void* d_ptr);
+/* stream-ordered allocation on the bound stream from a pool that keeps freed memory (cudaMallocAsync): repeated
+ * proofs allocate their LDE-sized arrays without driver calls; bb_pool_trim synchronises and returns the memory */
+int bb_pool_alloc(void** d_ptr, size_t bytes);
+int bb_pool_free(void* d_ptr);
+int bb_pool_trim(void);
 int bb_h2d(void* d_dst, const void* h_src, size_t bytes);            /* async on the stream */
 int bb_d2h(void* h_dst, const void* d_src, size_t bytes);            /* async on the stream */
 int bb_d2d(void* d_dst, const void* d_src, size_t bytes);            /* async on the stream */

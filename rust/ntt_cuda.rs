@@ -57,6 +57,21 @@ mod cuda {
         fn bb_merkle_open_batch_device(d_nodes: *const u8, nleaves: usize, indices: *const u64, nq: usize, paths_out: *mut u8,
                                        pos_out: *mut u8, depth_out: *mut usize) -> CudaError;
         fn bb_gather_device(d_src: *const c_void, elem_bytes: usize, indices: *const u64, nq: usize, out: *mut c_void) -> CudaError;
+        // the rest of what a device-resident StarkProver::generate_proof calls (toyni_b200/host/toyni_prover.hpp is that loop
+        // in C++)
+        fn bb_pool_alloc(d_ptr: *mut *mut c_void, bytes: usize) -> CudaError;
+        fn bb_pool_free(d_ptr: *mut c_void) -> CudaError;
+        fn bb_h2d(d_dst: *mut c_void, h_src: *const c_void, bytes: usize) -> CudaError;
+        fn bb_d2h(h_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> CudaError;
+        fn bb_d2d(d_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> CudaError;
+        fn bb_sync() -> CudaError;
+        fn bb_coset_fft_device(d_coeffs: *const u32, n_coeffs: usize, log_size: u32, shift: u32, limbs: i32, d_out: *mut u32) -> CudaError;
+        fn bb_coset_ifft_device(d_evals: *mut u32, log_size: u32, shift: u32, limbs: i32) -> CudaError;
+        fn bb_merkle_commit_device(d_vals: *const u32, limbs: i32, n: usize, d_salts: *const u8, d_nodes: *mut u8, root_out: *mut u8) -> CudaError;
+        fn bb_fri_commit_device(d_layer0: *const u32, n: usize, shift: u32, final_size: usize, limbs: i32, d_salts: *const u8,
+                                challenge: Option<extern "C" fn(user: *mut c_void, root: *const u8, layer: u32, beta_out: *mut u32)>,
+                                user: *mut c_void, betas_in: *const u32, d_layers: *mut u32, d_nodes: *mut u8, roots_out: *mut u8,
+                                folds_out: *mut usize) -> CudaError;
         // one process, G devices (header section 4)
         fn bb_mg_init(ngpus: i32, mg_out: *mut *mut c_void) -> CudaError;
         fn bb_mg_destroy(mg: *mut c_void);

@@ -321,6 +321,35 @@ def test_fourstep_paths_on_one_gpu(D, log_n):
         fs.close()
 
 
+def test_fourstep_two_transforms_in_flight(D):
+    """FourStepFused.run_async: consecutive transforms alternate over two internal streams and three receive buffers (the
+    exchange of one beside the row passes of the previous one).  Five different vectors, outputs consumed one call late,
+    then the serial form again on the same object; world = 1 here, world > 1 in tools/mg_check.py / bench.py."""
+    import torch
+    from toyni_b200 import multigpu as MG
+    log_n = 18
+    xs = [O.random_field(1 << log_n, seed=900 + i) for i in range(5)]
+    refs = [O.ntt(x, threads=4) for x in xs]
+    fs = MG.FourStepFused(log_n, 0, 1)
+    pend, got = [], []
+    for x in xs:
+        pend.append(fs.run_async(D.to_device(MG.fourstep_scatter(x, 0, 1))))
+        if len(pend) == 2:
+            o, ev = pend.pop(0)
+            torch.cuda.current_stream().wait_event(ev)
+            got.append(MG.fourstep_gather([D.to_host(o)], log_n))
+    for o, ev in pend:
+        torch.cuda.current_stream().wait_event(ev)
+        got.append(MG.fourstep_gather([D.to_host(o)], log_n))
+    fs.join()
+    for g, r in zip(got, refs):
+        assert np.array_equal(g, r)
+    out = fs.run(D.to_device(MG.fourstep_scatter(xs[0], 0, 1)))
+    assert np.array_equal(MG.fourstep_gather([D.to_host(out)], log_n), refs[0])
+    fs.check_peers()
+    fs.close()
+
+
 def test_two_contexts_on_two_threads_do_not_share_scratch():
     """The reference's context is not re-entrant and its callers are single threaded (src/ntt.rs:118-120); here two
     sizes driven from two host threads at once must both come out right (per-context stream and scratch)."""

@@ -39,6 +39,31 @@ for log_n in (14, 16, 20, 22):
         if rank == 0: print(f"fused fourstep log_n={log_n} inv={inv} world={world}: {'OK' if good else 'FAIL'}", flush=True)
     fs.check_peers()
     fs.close()
+# two transforms in flight (run_async): six different vectors, outputs read in issue order
+for log_n in (16, 22):
+    n = 1 << log_n
+    fs = MG.FourStepFused(log_n, rank, world)
+    n1, n2 = MG.fourstep_split(log_n, world)
+    k1 = np.arange(rank * n1 // world, (rank + 1) * n1 // world)
+    xs_ = [O.random_field(n, seed=500 + log_n + i) for i in range(6)]
+    wants = [O.ntt(x, threads=4).reshape(n2, n1)[:, k1].T for x in xs_]
+    pend, good, got_n = [], True, 0
+    for i in range(6):
+        pend.append(fs.run_async(D.to_device(MG.fourstep_scatter(xs_[i], rank, world))))
+        if len(pend) == 2:
+            o, ev = pend.pop(0)
+            torch.cuda.current_stream().wait_event(ev)
+            good &= np.array_equal(D.to_host(o), wants[got_n]); got_n += 1
+    for o, ev in pend:
+        torch.cuda.current_stream().wait_event(ev)
+        good &= np.array_equal(D.to_host(o), wants[got_n]); got_n += 1
+    fs.join()
+    out = fs.run(D.to_device(MG.fourstep_scatter(xs_[0], rank, world)))  # back to the serial form on the same object
+    good &= np.array_equal(D.to_host(out), wants[0])
+    fs.check_peers()
+    fs.close()
+    ok &= good
+    if rank == 0: print(f"pipelined fused fourstep log_n={log_n} world={world}: {'OK' if good else 'FAIL'}", flush=True)
 # cyclic fold chain
 m_log = 14
 ee = O.random_field(4 << m_log, seed=3).reshape(1 << m_log, 4)

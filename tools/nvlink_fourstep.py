@@ -104,7 +104,7 @@ for i in range(K):
     block = blocks[i % 3]
     _bind_stream()
     fs.epoch += 1
-    k = fs.epoch & 1
+    k = fs.epoch % fs.NBUF
     ev[i][0].record()
     check(L.bb_ntt_columns_scatter_device(_chk(block), LOG_N, n1.bit_length() - 1, cw, 0, fs.peers[k], world, rank),
           "bb_ntt_columns_scatter_device")
@@ -120,10 +120,26 @@ ph = [sum(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(5, K)) / (K - 5) fo
 phases = {"column_passes_with_peer_stores_ms": max_over_ranks(ph[0]), "signal_and_wait_ms": max_over_ranks(ph[1]),
           "row_passes_ms": max_over_ranks(ph[2]),
           "note": "max over ranks of each phase's mean; the wait absorbs the skew between ranks and the drain of the peer stores"}
+# 3. two transforms in flight (run_async)
+ms_pipe = None
+if fs.NBUF >= 3:
+    for i in range(4):
+        fs.run_async(blocks[i % 3])
+    fs.join()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(K):
+        fs.run_async(blocks[i % 3])
+    fs.join()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_pipe = max_over_ranks(e0.elapsed_time(e1) / K)
+fs.check_peers()
 fs.close()
 if rank == 0:
     sent = (n // world) * (world - 1) // world * 4
-    print(json.dumps({"world": world, "log_n": LOG_N, "n1": n1, "n2": n2, "transforms": K, "ms_per_transform": ms,
+    print(json.dumps({"world": world, "nbuf": fs.NBUF, "log_n": LOG_N, "n1": n1, "n2": n2, "transforms": K, "ms_per_transform": ms, "ms_per_transform_two_in_flight": ms_pipe,
                       "nvlink_gbs_per_gpu_over_whole_transform": sent / (ms * 1e-3) / 1e9,
                       "nvlink_gbs_per_gpu_over_column_phase": sent / (phases["column_passes_with_peer_stores_ms"] * 1e-3) / 1e9,
                       "links": links, "phases": phases}))

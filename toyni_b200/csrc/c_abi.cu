@@ -218,6 +218,39 @@ int bb_sync(void) { return note((int)cudaStreamSynchronize(cur_stream())); }
 
 int bb_dev_alloc(void** d_ptr, size_t bytes) { return note((int)cudaMalloc(d_ptr, bytes)); }
 int bb_dev_free(void* d_ptr) { return note((int)cudaFree(d_ptr)); }
+// Stream-ordered allocations from the device's default memory pool, which is told to keep what is freed: a prover that
+// allocates its LDE-sized arrays per proof (toyni_prover.hpp) pays the driver once, not 10+ ms of cudaMalloc / cudaFree
+// of multi-gigabyte buffers per proof.
+static int pool_ready() {
+    static std::atomic<int> done[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (done[dev & 63].load()) return 0;
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e != cudaSuccess) return (int)e;
+    uint64_t keep = UINT64_MAX;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e != cudaSuccess) return (int)e;
+    done[dev & 63].store(1);
+    return 0;
+}
+int bb_pool_alloc(void** d_ptr, size_t bytes) {
+    int rc = pool_ready();
+    if (rc) return note(rc);
+    return note((int)cudaMallocAsync(d_ptr, bytes ? bytes : 1, cur_stream()));
+}
+int bb_pool_free(void* d_ptr) { return d_ptr ? note((int)cudaFreeAsync(d_ptr, cur_stream())) : 0; }
+int bb_pool_trim(void) {
+    int dev = 0;
+    cudaMemPool_t pool;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cur_stream());
+    if (e == cudaSuccess) e = cudaMemPoolTrimTo(pool, 0);
+    return note((int)e);
+}
 int bb_h2d(void* d_dst, const void* h_src, size_t bytes) {
     return note((int)cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, cur_stream()));
 }

@@ -66,8 +66,10 @@ __global__ void __launch_bounds__(LDE::NT, 1) lde_expand_kernel(const LdeParams 
     asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 
     const uint32_t nrows = (p.n_coeffs + 4095u) >> 12;
-    // inputs of one tile: thread `tid` brings row i1 = tid, four columns, already multiplied by shift^i
-    auto stage_inputs = [&](uint32_t tile, uint32_t buf) {
+    // Inputs of one tile: thread `tid` brings row i1 = tid, four columns, multiplied by shift^i.  The load is issued before
+    // round A and used after it; the power of the shift is a running product from tile to tile (one table look-up per
+    // thread and kernel: field arithmetic is exact, a running product gives the same bits).
+    auto fetch = [&](uint32_t tile) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         const uint32_t idx = (tid << 12) + 4u * tile;
         if (tid < nrows) {
@@ -78,23 +80,40 @@ __global__ void __launch_bounds__(LDE::NT, 1) lde_expand_kernel(const LdeParams 
                 if (idx + 1u < p.n_coeffs) v.y = __ldg(p.in + idx + 1u);
                 if (idx + 2u < p.n_coeffs) v.z = __ldg(p.in + idx + 2u);
             }
-            if (p.has_shift) {
-                v.x = monty_mul(v.x, pow_lookup(p.shift, idx));
-                v.y = monty_mul(v.y, pow_lookup(p.shift, idx + 1u));
-                v.z = monty_mul(v.z, pow_lookup(p.shift, idx + 2u));
-                v.w = monty_mul(v.w, pow_lookup(p.shift, idx + 3u));
-            }
+        }
+        return v;
+    };
+    uint32_t tile = blockIdx.x, it = 0;
+    uint32_t pw = 0, pw_step = 0, s1 = 0;  // Montgomery forms of shift^(4096 tid + 4 tile), shift^(4 gridDim), shift
+    if (p.has_shift && tid < nrows && tile < p.total_tiles) {
+        pw = pow_lookup(p.shift, (tid << 12) + 4u * tile);
+        pw_step = pow_lookup(p.shift, 4u * gridDim.x);
+        s1 = pow_lookup(p.shift, 1u);
+    }
+    auto stage = [&](uint4 v, uint32_t buf) {
+        if (p.has_shift && tid < nrows) {
+            uint32_t q = pw;
+            v.x = monty_mul(v.x, q);
+            q = monty_mul(q, s1);
+            v.y = monty_mul(v.y, q);
+            q = monty_mul(q, s1);
+            v.z = monty_mul(v.z, q);
+            q = monty_mul(q, s1);
+            v.w = monty_mul(v.w, q);
+            pw = monty_mul(pw, pw_step);
         }
         reinterpret_cast<uint4*>(smem + LDE::OFF_IN)[buf * 512u + tid] = v;
     };
 
     uint4* tile_s = reinterpret_cast<uint4*>(smem + LDE::OFF_TILE);
     const uint2* tw_s = reinterpret_cast<const uint2*>(smem + LDE::OFF_TW);
-    uint32_t tile = blockIdx.x, it = 0;
-    if (tile < p.total_tiles) stage_inputs(tile, 0u);
+    if (tile < p.total_tiles) stage(fetch(tile), 0u);
+    __syncthreads();
     while (tile < p.total_tiles) {
         const uint32_t next = tile + gridDim.x;
-        __syncthreads();  // inputs of this tile are staged; every warp has taken the previous tile out of the tile buffer
+        const bool have_next = next < p.total_tiles;
+        uint4 nx = make_uint4(0u, 0u, 0u, 0u);
+        if (have_next) nx = fetch(next);
         {   // round A: b = warp, c = lane
             const uint4* xin = reinterpret_cast<const uint4*>(smem + LDE::OFF_IN) + (it & 1u) * 512u;
             uint4 x[16];
@@ -121,12 +140,15 @@ __global__ void __launch_bounds__(LDE::NT, 1) lde_expand_kernel(const LdeParams 
 #pragma unroll
             for (int k = 0; k < 16; k++) tile_s[(k * 16u + warp) * 32u + lane] = x[k];
         }
-        if (next < p.total_tiles) stage_inputs(next, (it + 1u) & 1u);
-        __syncthreads();
+        if (have_next) stage(nx, (it + 1u) & 1u);
+        __syncthreads();  // the tile is complete; the inputs of the next tile are staged
         {   // round B: a' = warp, c = lane
             uint4 x[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) x[k] = tile_s[(warp * 16u + v7_brev4(k)) * 32u + lane];
+            // every warp holds its part of the tile in registers: the buffer is free for round A of the next tile, which a
+            // warp starts as soon as its own stores below are issued — stores and arithmetic of neighbouring tiles overlap
+            __syncthreads();
             const uint32_t H = 32u * warp + lane;
             lde_dit16(x, [&](int t, int kp) { return tw_s[(H + 512u * kp) << (3 - t)]; });
             uint32_t* o = p.out + ((size_t)(4u * tile) << LDE::LOG_ROWS) + 32u * warp + lane;

@@ -11,6 +11,7 @@
 // reproducible and comparable byte for byte (toyni::serialize_proof) with the CPU oracle's and with
 // toyni_b200/prover.py, which is the same loop in Python.  No CPU fallback: without a device every call throws.
 #pragma once
+#include <chrono>
 #include <cstring>
 
 #include "toyni.hpp"
@@ -72,14 +73,15 @@ class Sha256 {
     }
 };
 
-/// Device allocation through the ABI (bb_dev_alloc / bb_dev_free), freed on scope exit.
+/// Device allocation through the ABI (bb_pool_alloc / bb_pool_free: stream ordered, cached between proofs), freed on
+/// scope exit.
 template <typename T>
 class DevBuf {
   public:
     DevBuf() = default;
     explicit DevBuf(size_t count) : n_(count) {
         void* p = nullptr;
-        check(bb_dev_alloc(&p, (count ? count : 1) * sizeof(T)), "bb_dev_alloc");
+        check(bb_pool_alloc(&p, (count ? count : 1) * sizeof(T)), "bb_pool_alloc");
         p_ = static_cast<T*>(p);
     }
     DevBuf(const DevBuf&) = delete;
@@ -96,7 +98,7 @@ class DevBuf {
     }
     ~DevBuf() { reset(); }
     void reset() {
-        if (p_) bb_dev_free(p_);
+        if (p_) bb_pool_free(p_);
         p_ = nullptr;
     }
     T* get() const { return p_; }
@@ -227,6 +229,9 @@ class StarkProver {
   public:
     explicit StarkProver(std::vector<BabyBear> trace_column) : trace_(std::move(trace_column)) {}
 
+    /// When set, generate_proof* synchronises the device after every stage and records (stage, milliseconds) here.
+    mutable std::vector<std::pair<const char*, double>>* stage_timings = nullptr;
+
     StarkProof generate_proof(const std::vector<BabyBear>& mask, const std::vector<uint8_t>& salts_trace,
                               const std::vector<uint8_t>& salts_quot, const std::vector<uint8_t>& salts_fri) const {
         using namespace detail;
@@ -259,26 +264,49 @@ class StarkProver {
         if (salts_fri_bytes < fri_salt_bytes(lde, final_size)) throw std::logic_error("salts_fri too short");
         const uint64_t g = get_root_of_unity(log_t).value;
         const uint32_t shift = (uint32_t)COSET_SHIFT;
+        auto t_last = std::chrono::steady_clock::now();
+        auto mark = [&](const char* stage) {
+            if (!stage_timings) return;
+            check(bb_sync(), "bb_sync");
+            auto now = std::chrono::steady_clock::now();
+            stage_timings->emplace_back(stage, std::chrono::duration<double, std::milli>(now - t_last).count());
+            t_last = now;
+        };
 
-        // 1. trace polynomial: INTT on the device, then T + Z_H * R on the host (:110-121)
+        // 1. trace polynomial: INTT on the device, then T + Z_H * R (:110-121).  Z_H * R = X^n R - R touches the first and
+        //    the last MASK_DEGREE coefficients only: those 2 x 140 values are patched from the host, the 2^k coefficients
+        //    in between never leave the device.
         std::vector<uint32_t> h32(trace_len);
         for (size_t i = 0; i < trace_len; i++) h32[i] = (uint32_t)(trace_[i].value % BABYBEAR_PRIME);
-        DevBuf<uint32_t> d_interp(trace_len);
-        d_interp.upload(h32.data(), trace_len);
-        check(bb_coset_ifft_device(d_interp.get(), log_t, 1, 1), "bb_coset_ifft_device");
-        check(bb_d2h(h32.data(), d_interp.get(), trace_len * 4), "bb_d2h");
-        check(bb_sync(), "bb_sync");
-        std::vector<uint32_t> tp(trace_len + MASK_DEGREE, 0);
-        for (size_t i = 0; i < trace_len; i++) tp[i] = h32[i];
-        for (size_t i = 0; i < MASK_DEGREE; i++) {  // Z_H * R = X^n R - R
-            uint64_t m = mask[i].value % BABYBEAR_PRIME;
-            tp[trace_len + i] = (uint32_t)addm(tp[trace_len + i], m);
-            tp[i] = (uint32_t)subm(tp[i], m);
+        DevBuf<uint32_t> d_tpoly(trace_len + MASK_DEGREE);
+        d_tpoly.upload(h32.data(), trace_len);
+        check(bb_coset_ifft_device(d_tpoly.get(), log_t, 1, 1), "bb_coset_ifft_device");
+        size_t n_tp = trace_len + MASK_DEGREE;
+        if (trace_len >= MASK_DEGREE && mask[MASK_DEGREE - 1].value % BABYBEAR_PRIME != 0) {
+            uint32_t head[MASK_DEGREE], tail[MASK_DEGREE];
+            check(bb_d2h(head, d_tpoly.get(), sizeof head), "bb_d2h");
+            check(bb_sync(), "bb_sync");
+            for (size_t i = 0; i < MASK_DEGREE; i++) {
+                const uint64_t m = mask[i].value % BABYBEAR_PRIME;
+                head[i] = (uint32_t)subm(head[i], m);
+                tail[i] = (uint32_t)m;
+            }
+            check(bb_h2d(d_tpoly.get(), head, sizeof head), "bb_h2d");
+            check(bb_h2d(d_tpoly.get() + trace_len, tail, sizeof tail), "bb_h2d");
+            check(bb_sync(), "bb_sync");  // head / tail live on this stack frame
+        } else {  // short traces (the two ranges overlap) or a zero leading mask coefficient (the polynomial is trimmed)
+            check(bb_d2h(h32.data(), d_tpoly.get(), trace_len * 4), "bb_d2h");
+            check(bb_sync(), "bb_sync");
+            std::vector<uint32_t> tp(trace_len + MASK_DEGREE, 0);
+            for (size_t i = 0; i < trace_len; i++) tp[i] = h32[i];
+            for (size_t i = 0; i < MASK_DEGREE; i++) {
+                const uint64_t m = mask[i].value % BABYBEAR_PRIME;
+                tp[trace_len + i] = (uint32_t)addm(tp[trace_len + i], m);
+                tp[i] = (uint32_t)subm(tp[i], m);
+            }
+            while (n_tp > 0 && tp[n_tp - 1] == 0) n_tp--;  // Polynomial::new trims, src/math/polynomial.rs:11-16
+            d_tpoly.upload(tp.data(), n_tp);
         }
-        size_t n_tp = tp.size();
-        while (n_tp > 0 && tp[n_tp - 1] == 0) n_tp--;  // Polynomial::new trims, src/math/polynomial.rs:11-16
-        DevBuf<uint32_t> d_tpoly(n_tp);
-        d_tpoly.upload(tp.data(), n_tp);
         // LDE over the shifted domain + salted commit (:124-130)
         DevBuf<uint32_t> d_tlde(lde);
         check(bb_coset_fft_device(d_tpoly.get(), n_tp, log_lde, shift, 1, d_tlde.get()), "bb_coset_fft_device");
@@ -288,6 +316,8 @@ class StarkProver {
         const size_t nodes_lde = bb_merkle_node_count(lde);
         DevBuf<uint8_t> d_nodes_t(nodes_lde * 32), d_nodes_q(nodes_lde * 32);
         check(bb_merkle_commit_device(d_tlde.get(), 1, lde, d_salts_trace, d_nodes_t.get(), proof.trace_commitment.data()), "trace commit");
+
+        mark("interpolate + LDE + trace commit");
 
         // 2. constraint and quotient (:133-153): Z_H over the coset takes BLOWUP values, 7^n (w_N^n)^i - 1
         const uint64_t b1 = pow_mod(g, trace_len - 1), b2 = pow_mod(g, trace_len - 2);
@@ -302,6 +332,8 @@ class StarkProver {
         copy_device(d_qcoef.get(), d_q.get(), lde);
         check(bb_coset_ifft_device(d_qcoef.get(), log_lde, shift, 1), "bb_coset_ifft_device");
         check(bb_merkle_commit_device(d_q.get(), 1, lde, d_salts_quot, d_nodes_q.get(), proof.quotient_commitment.data()), "quotient commit");
+
+        mark("constraint + quotient + quotient commit");
 
         // 3. z outside both domains (:156-161, :378-399): z^N != 1 and (z / 7)^N != 1
         FiatShamirTranscript tr;
@@ -327,6 +359,8 @@ class StarkProver {
         proof.t_ggz = BabyBear{t_ggz};
         proof.q_z = BabyBear{q_z};
         for (BabyBear v : {proof.t_z, proof.t_gz, proof.t_ggz, proof.q_z}) tr.absorb_field(v);
+
+        mark("z + out-of-domain evaluations");
 
         // 5. DEEP polynomial (:186-198)
         DevBuf<uint32_t> d_deep(lde);
@@ -372,6 +406,8 @@ class StarkProver {
             }
         }
 
+        mark("DEEP + FRI commit loop");
+
         // 7. query phase (:250-295): one batched opening per tree
         const std::vector<uint64_t> queries = tr.squeeze_indices(NUM_QUERIES, lde / 2);
         const DeviceTree trace_tree{d_tlde.get(), d_nodes_t.get(), d_salts_trace, lde};
@@ -415,6 +451,7 @@ class StarkProver {
         check(bb_d2h(fin.data(), trees.back().vals, fin.size() * 4), "bb_d2h");
         check(bb_sync(), "bb_sync");
         for (uint32_t v : fin) proof.fri_final_layer.push_back(BabyBear{v});
+        mark("queries: openings + proof object");
         return proof;
     }
 

@@ -38,6 +38,9 @@ _SIGNATURES = {
     "bb_sync": ([], C.c_int),
     "bb_dev_alloc": ([C.POINTER(C.c_void_p), C.c_size_t], C.c_int),
     "bb_dev_free": ([C.c_void_p], C.c_int),
+    "bb_pool_alloc": ([C.POINTER(C.c_void_p), C.c_size_t], C.c_int),
+    "bb_pool_free": ([C.c_void_p], C.c_int),
+    "bb_pool_trim": ([], C.c_int),
     "bb_h2d": ([C.c_void_p, C.c_void_p, C.c_size_t], C.c_int),
     "bb_d2h": ([C.c_void_p, C.c_void_p, C.c_size_t], C.c_int),
     "bb_d2d": ([C.c_void_p, C.c_void_p, C.c_size_t], C.c_int),

@@ -157,23 +157,33 @@ class FourStepFused:
     rank that owns it (CUDA-IPC peer mappings: the stores travel over NVLink / NVSwitch), already in the layout the
     row transforms read.  Compared with `fourstep_ntt_cuda` this removes the twiddle pass, the NCCL all-to-all and
     the re-layout copy.  The ranks rendezvous on the device (flag words in peer memory, one signal + one wait kernel
-    per transform, receive buffers double buffered), so a transform involves no host synchronisation and no NCCL
-    call; torch.distributed is used once, to exchange the IPC handles."""
+    per transform, three receive buffers in rotation), so a transform involves no host synchronisation and no NCCL
+    call; torch.distributed is used once, to exchange the IPC handles.
+
+    `run` executes one transform on the caller's stream.  `run_async` keeps TWO transforms in flight on two internal
+    streams: the column passes of transform e (whose last pass is bound by the NVLink stores) overlap the row passes of
+    transform e-1, which only use the SMs; `join` makes the caller's stream wait for everything issued."""
+
+    NBUF = 3
 
     FLAG_WORDS = 512  # 8 lines of 32 words for the flags, then the error word
 
-    def __init__(self, log_n, rank, world):
+    def __init__(self, log_n, rank, world, nbuf=None):
         import ctypes as C
 
         from .lib import check, lib
         self.log_n, self.rank, self.world = log_n, rank, world
+        # receive buffers in rotation: 2 suffice for `run`, `run_async` needs 3 (see its contract)
+        self.NBUF = int(nbuf or os.environ.get("TOYNI_FOURSTEP_NBUF", 3))
+        assert self.NBUF in (2, 3)
         self.n1, self.n2 = fourstep_split(log_n, world)
         self.rw, self.cw = self.n1 // world, self.n2 // world
         self.buf_words = self.rw * self.n2
-        # one allocation per rank: [receive buffer 0][receive buffer 1][flags + error word]
-        self.mem = _RawCudaBuffer(2 * self.buf_words + self.FLAG_WORDS)
-        whole = self.mem.tensor((2 * self.buf_words + self.FLAG_WORDS,))
-        whole[2 * self.buf_words:].zero_()
+        # one allocation per rank: [receive buffers 0 .. NBUF-1][flags + error word]
+        nb = self.NBUF
+        self.mem = _RawCudaBuffer(nb * self.buf_words + self.FLAG_WORDS)
+        whole = self.mem.tensor((nb * self.buf_words + self.FLAG_WORDS,))
+        whole[nb * self.buf_words:].zero_()
         torch.cuda.synchronize()
         handle = (C.c_uint8 * 64)()
         check(lib().bb_ipc_get_handle(self.mem.ptr, handle), "bb_ipc_get_handle")
@@ -194,30 +204,35 @@ class FourStepFused:
                 check(lib().bb_ipc_open_handle(hb, C.byref(p)), "bb_ipc_open_handle")
                 base.append(p.value)
                 self._opened.append(p)
-        self.peers = [(C.c_void_p * world)(*[b + 4 * k * self.buf_words for b in base]) for k in range(2)]
-        flag_ptrs = [b + 4 * 2 * self.buf_words for b in base]
+        self.peers = [(C.c_void_p * world)(*[b + 4 * k * self.buf_words for b in base]) for k in range(nb)]
+        flag_ptrs = [b + 4 * nb * self.buf_words for b in base]
         self.d_peer_flags = torch.tensor(flag_ptrs, dtype=torch.int64, device="cuda")  # device array of pointers
-        self.flags_ptr = C.c_void_p(base[rank] + 4 * 2 * self.buf_words)
-        self.err_ptr = C.c_void_p(base[rank] + 4 * (2 * self.buf_words + 256))
-        self.err = whole[2 * self.buf_words + 256:2 * self.buf_words + 257]
-        self.out = [whole[k * self.buf_words:(k + 1) * self.buf_words].view(self.rw, self.n2) for k in range(2)]
+        self.flags_ptr = C.c_void_p(base[rank] + 4 * nb * self.buf_words)
+        self.err_ptr = C.c_void_p(base[rank] + 4 * (nb * self.buf_words + 256))
+        self.err = whole[nb * self.buf_words + 256:nb * self.buf_words + 257]
+        self.out = [whole[k * self.buf_words:(k + 1) * self.buf_words].view(self.rw, self.n2) for k in range(nb)]
         self.epoch = 0
+        self._streams = None   # run_async: two internal streams, events "peers waited" / "rows done" per epoch parity
+        self._ev_waited = [None, None]
+        self._ev_rows = [None, None]
         if world > 1:
             dist.barrier()  # every rank has mapped every buffer and zeroed its flags
 
     def run(self, block, inverse=False):
         """block: int32 CUDA tensor (n1, n2/G), this rank's columns (destroyed).  Returns the (n1/G, n2) receive
-        buffer holding out[k1_local][k2] = X[k1 + n1*k2]; it stays valid for the next transform (double buffered)."""
+        buffer holding out[k1_local][k2] = X[k1 + n1*k2]; it stays valid until the transform after next is started."""
         import ctypes as C
 
         from .device import _bind_stream, _chk, ntt_batch_
         from .lib import check, lib
         assert tuple(block.shape) == (self.n1, self.cw)
         _bind_stream()
+        if self._ev_rows[0] is not None:  # transforms issued by run_async may still be running on the internal streams
+            self.join()
         self.epoch += 1
-        k = self.epoch & 1
+        k = self.epoch % self.NBUF
         L = lib()
-        # buffer k was last read by the row transforms of epoch-2; every rank finished those before it signalled
+        # buffer k was last read by the row transforms of epoch-3; every rank finished those before it signalled
         # epoch-1, and this rank has already waited for all epoch-1 signals: the peers' buffers are free
         check(L.bb_ntt_columns_scatter_device(_chk(block), self.log_n, self.n1.bit_length() - 1, self.cw,
                                               1 if inverse else 0, self.peers[k], self.world, self.rank),
@@ -226,6 +241,59 @@ class FourStepFused:
               "bb_peer_signal_device")
         check(L.bb_peer_wait_device(self.flags_ptr, self.world, self.epoch, self.err_ptr), "bb_peer_wait_device")
         return ntt_batch_(self.out[k], inverse)
+
+    def run_async(self, block, inverse=False):
+        """Same transform, issued on one of two internal streams (alternating), so that consecutive calls overlap: the
+        column passes + NVLink stores of this transform run beside the row passes of the previous one.  Returns
+        (out, done): `out` as for `run`, `done` a CUDA event recorded after the row passes.  Contract: `block` was
+        produced on the caller's current stream; `out` must have been consumed (work enqueued on the caller's stream
+        after waiting for `done`) before run_async is called for the second time after this call."""
+        import ctypes as C
+
+        from .device import _bind_stream, _chk, ntt_batch_
+        from .lib import check, lib
+        assert tuple(block.shape) == (self.n1, self.cw)
+        assert self.NBUF >= 3, "run_async needs three receive buffers (FourStepFused(..., nbuf=3))"
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        self.epoch += 1
+        e = self.epoch
+        k, par = e % self.NBUF, e & 1
+        st = self._streams[par]
+        L = lib()
+        ready = torch.cuda.Event()
+        ready.record()  # the caller's stream: the input block exists, and what the caller consumed so far is ordered
+        with torch.cuda.stream(st):
+            st.wait_event(ready)
+            # all peers have signalled e-1 (they are done reading buffer k, last used by epoch e-3) once the OTHER
+            # stream's wait kernel of e-1 has returned
+            if self._ev_waited[par ^ 1] is not None:
+                st.wait_event(self._ev_waited[par ^ 1])
+            _bind_stream()
+            check(L.bb_ntt_columns_scatter_device(_chk(block), self.log_n, self.n1.bit_length() - 1, self.cw,
+                                                  1 if inverse else 0, self.peers[k], self.world, self.rank),
+                  "bb_ntt_columns_scatter_device")
+            # our signal of e tells the peers that our row passes of e-1 are finished
+            if self._ev_rows[par ^ 1] is not None:
+                st.wait_event(self._ev_rows[par ^ 1])
+            check(L.bb_peer_signal_device(C.c_void_p(self.d_peer_flags.data_ptr()), self.world, self.rank, e), "bb_peer_signal_device")
+            check(L.bb_peer_wait_device(self.flags_ptr, self.world, e, self.err_ptr), "bb_peer_wait_device")
+            self._ev_waited[par] = torch.cuda.Event()
+            self._ev_waited[par].record(st)
+            out = ntt_batch_(self.out[k], inverse)
+            self._ev_rows[par] = torch.cuda.Event()
+            self._ev_rows[par].record(st)
+        _bind_stream()
+        return out, self._ev_rows[par]
+
+    def join(self):
+        """The caller's current stream waits for every transform issued by run_async."""
+        cur = torch.cuda.current_stream()
+        for ev in self._ev_rows:
+            if ev is not None:
+                cur.wait_event(ev)
+        self._ev_rows = [None, None]
+        self._ev_waited = [None, None]
 
     def check_peers(self):
         """Host-side check (synchronises): raises if a wait kernel gave up on a peer."""
