@@ -280,26 +280,6 @@ def sharded_fourstep27(c, steps):
         it[0] += 1
     ms = c.time_ms(step, steps, warm=3)
     fused.check_peers()
-    # two transforms in flight (FourStepFused.run_async): the column passes + NVLink stores of one beside the row passes
-    # of the previous one.  Parity first: four pipelined transforms of the same block give the digest checked above.
-    pipe_ok = True
-    pending = []
-    for i in range(4):
-        pending.append(fused.run_async(block.clone()))
-        if len(pending) == 2:
-            o, ev = pending.pop(0)
-            torch.cuda.current_stream().wait_event(ev)
-            pipe_ok &= _sha(o) == digests[c.rank][0]
-    for o, ev in pending:
-        torch.cuda.current_stream().wait_event(ev)
-        pipe_ok &= _sha(o) == digests[c.rank][0]
-    fused.join()
-    pipe_ok = c.min_over_ranks(pipe_ok)
-
-    def step_async():
-        fused.run_async(work[it[0] % 3])
-        it[0] += 1
-    ms_pipe = c.time_ms(step_async, steps, warm=4, join=fused.join)
     fused.check_peers()
     fused.close()
     sent = (n // c.world) * (c.world - 1) // c.world * 4
@@ -309,11 +289,7 @@ def sharded_fourstep27(c, steps):
             "nvlink_bytes_sent_per_gpu": sent, "nvlink_gbs_per_gpu": gbs,
             "nvlink_frac_of_measured_770": gbs / NVLINK_MEASURED_GBS, "nvlink_frac_of_nominal_900": gbs / 900.0,
             "nvlink_note": "bytes this GPU stores to its peers / time of the WHOLE transform (not a link counter)",
-            "single_gpu_2^27_ms": t_single, "speedup_vs_single_gpu": t_single / ms,
-            "pipelined_ms": ms_pipe, "pipelined_gelem_s": n / (ms_pipe * 1e-3) / 1e9, "pipelined_speedup_vs_single_gpu": t_single / ms_pipe,
-            "pipelined_parity_ok": pipe_ok,
-            "pipelined_note": "ms per transform with two transforms in flight on two streams (throughput); `ms` is one transform at a time (latency)",
-            "steps": steps, "parity_ok": parity,
+            "single_gpu_2^27_ms": t_single, "speedup_vs_single_gpu": t_single / ms, "steps": steps, "parity_ok": parity,
             "parity": "every output slab of every rank, SHA-256 against the CPU oracle on the same seeded input"}
 
 

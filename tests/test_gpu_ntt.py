@@ -330,7 +330,7 @@ def test_fourstep_two_transforms_in_flight(D):
     log_n = 18
     xs = [O.random_field(1 << log_n, seed=900 + i) for i in range(5)]
     refs = [O.ntt(x, threads=4) for x in xs]
-    fs = MG.FourStepFused(log_n, 0, 1)
+    fs = MG.FourStepFused(log_n, 0, 1, nbuf=3)
     pend, got = [], []
     for x in xs:
         pend.append(fs.run_async(D.to_device(MG.fourstep_scatter(x, 0, 1))))

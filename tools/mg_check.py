@@ -42,7 +42,7 @@ for log_n in (14, 16, 20, 22):
 # two transforms in flight (run_async): six different vectors, outputs read in issue order
 for log_n in (16, 22):
     n = 1 << log_n
-    fs = MG.FourStepFused(log_n, rank, world)
+    fs = MG.FourStepFused(log_n, rank, world, nbuf=3)
     n1, n2 = MG.fourstep_split(log_n, world)
     k1 = np.arange(rank * n1 // world, (rank + 1) * n1 // world)
     xs_ = [O.random_field(n, seed=500 + log_n + i) for i in range(6)]

@@ -157,14 +157,14 @@ class FourStepFused:
     rank that owns it (CUDA-IPC peer mappings: the stores travel over NVLink / NVSwitch), already in the layout the
     row transforms read.  Compared with `fourstep_ntt_cuda` this removes the twiddle pass, the NCCL all-to-all and
     the re-layout copy.  The ranks rendezvous on the device (flag words in peer memory, one signal + one wait kernel
-    per transform, three receive buffers in rotation), so a transform involves no host synchronisation and no NCCL
+    per transform, two or three receive buffers in rotation), so a transform involves no host synchronisation and no NCCL
     call; torch.distributed is used once, to exchange the IPC handles.
 
-    `run` executes one transform on the caller's stream.  `run_async` keeps TWO transforms in flight on two internal
-    streams: the column passes of transform e (whose last pass is bound by the NVLink stores) overlap the row passes of
-    transform e-1, which only use the SMs; `join` makes the caller's stream wait for everything issued."""
-
-    NBUF = 3
+    `run` executes one transform on the caller's stream.  `run_async` (objects made with nbuf=3) keeps TWO transforms
+    in flight on two internal streams, so that the column passes of transform e could overlap the row passes of e-1;
+    `join` makes the caller's stream wait for everything issued.  Measured at 8 GPUs it gains nothing: the persistent
+    CTAs of the scattering pass hold every SM while they wait on their NVLink stores, so the other stream's row passes
+    only start when they drain."""
 
     FLAG_WORDS = 512  # 8 lines of 32 words for the flags, then the error word
 
@@ -173,8 +173,10 @@ class FourStepFused:
 
         from .lib import check, lib
         self.log_n, self.rank, self.world = log_n, rank, world
-        # receive buffers in rotation: 2 suffice for `run`, `run_async` needs 3 (see its contract)
-        self.NBUF = int(nbuf or os.environ.get("TOYNI_FOURSTEP_NBUF", 3))
+        # receive buffers in rotation: 2 for `run` (default), `run_async` needs 3 (see its contract).  Measured on 8 B200s
+        # at 2^27: 0.226 ms per transform with two buffers, 0.296 ms with three (the NVLink-store pass slows from 0.149 to
+        # 0.216 ms, profiles/fourstep_nbuf_ab_8gpu_r2.json) — so three are allocated only on request.
+        self.NBUF = int(nbuf or os.environ.get("TOYNI_FOURSTEP_NBUF", 2))
         assert self.NBUF in (2, 3)
         self.n1, self.n2 = fourstep_split(log_n, world)
         self.rw, self.cw = self.n1 // world, self.n2 // world
