@@ -1,5 +1,5 @@
 """Measure BASELINE.json configs 2-4 on one B200 (CUDA events, device-resident data) and print one JSON document.
-   python tools/measure_configs.py > profiles/configs_r1.json"""
+   python tools/measure_configs.py > profiles/configs_r2.json"""
 import json, sys, time
 import numpy as np
 import torch

@@ -468,14 +468,7 @@ int bb_fri_fold_xs_device(const uint32_t* d_evals, size_t m, const uint32_t* d_x
 
 size_t bb_merkle_node_count(size_t nleaves) { return merkle_node_count(nleaves); }
 
-static int levels_of(size_t n) {  // kernel launches of merkle_upper_levels: one per level above 2048 nodes, one for the rest
-    int l = 0;
-    while (n > 2048) {
-        n = (n + 1) / 2;
-        l++;
-    }
-    return l + (n > 1 ? 1 : 0);
-}
+static int levels_of(size_t n) { return merkle_upper_launches(n); }  // kernel launches of merkle_upper_levels
 
 static int root_to_host(const uint8_t* d_nodes, size_t n, uint8_t* root_out, cudaStream_t s) {
     CK(cudaMemcpyAsync(root_out, d_nodes + 32 * (merkle_node_count(n) - 1), 32, cudaMemcpyDeviceToHost, s));

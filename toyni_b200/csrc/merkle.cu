@@ -78,10 +78,31 @@ __global__ void __launch_bounds__(512) node_hash_smem_kernel(const uint8_t* __re
         node_hash_one<true>(child, parent, n_child, j, s_tab);
 }
 
-// Every remaining level of a small tree (n_child <= 2 * TAIL_THREADS) in ONE launch: a single CTA walks the levels
-// with a barrier between them.  The late FRI layers (and the top of every tree) are launch bound otherwise: one
-// kernel per level, 13 levels for 2^13 leaves.
-constexpr int TAIL_THREADS = 1024;
+// Below 2^18 nodes a level no longer fills the GPU and a tree is a chain of latencies: one hash (two compressions, ~2 us
+// of dependent instructions) per level, plus a launch and a drain if every level is its own kernel.  Two kernels
+// walk several levels per launch instead, with a block barrier between levels:
+//   subtree kernel: CTA b owns SUB_NODES consecutive nodes of a level whose size is a multiple of SUB_NODES and reduces
+//                   them to ONE node, eight levels up (every intermediate level has an exact power-of-two share per
+//                   CTA, so no odd-node duplication can occur inside); the CTAs of a launch spread over the SMs;
+//   tail kernel:    a single CTA finishes what is left (at most 2 * TAIL_THREADS nodes, any size, odd levels included).
+constexpr int SUB_LEVELS = 8, SUB_NODES = 1 << SUB_LEVELS, SUB_THREADS = SUB_NODES / 2;
+__global__ void __launch_bounds__(SUB_THREADS) node_hash_subtree_kernel(uint8_t* __restrict__ level, size_t n_child,
+                                                                        const uint32_t* __restrict__ pad_tab) {
+    size_t base = (size_t)blockIdx.x * SUB_NODES;  // this CTA's first node of the current level
+    uint32_t mine = SUB_NODES;                     // and how many it owns there
+#pragma unroll 1
+    for (int l = 0; l < SUB_LEVELS; l++) {
+        uint8_t* parent = level + 32 * n_child;
+        if (threadIdx.x < mine / 2) node_hash_one(level, parent, n_child, base / 2 + threadIdx.x, pad_tab);
+        __syncthreads();  // block-scope ordering of the global stores above with the loads of the next level
+        level = parent;
+        n_child /= 2;
+        base /= 2;
+        mine /= 2;
+    }
+}
+
+constexpr int TAIL_THREADS = 128;
 __global__ void __launch_bounds__(TAIL_THREADS) node_hash_tail_kernel(uint8_t* __restrict__ level, size_t n_child,
                                                                       const uint32_t* __restrict__ pad_tab) {
     while (n_child > 1) {
@@ -184,6 +205,18 @@ static int pad_table_get(const uint32_t** out) {
     return 0;
 }
 
+int merkle_upper_launches(size_t n) {  // kernel launches of merkle_upper_levels(n): the same walk, counting
+    int launches = 0;
+    while (n > (size_t)2 * TAIL_THREADS) {
+        if ((n + 1) / 2 < ((size_t)1 << 18) && n % SUB_NODES == 0)
+            n >>= SUB_LEVELS;
+        else
+            n = (n + 1) / 2;
+        launches++;
+    }
+    return launches + (n > 1 ? 1 : 0);
+}
+
 int merkle_upper_levels(uint8_t* d_nodes, size_t n, cudaStream_t s) {
     const uint32_t* pad_tab = nullptr;
     if (n > 1) {
@@ -210,6 +243,14 @@ int merkle_upper_levels(uint8_t* d_nodes, size_t n, cudaStream_t s) {
                 cur_n = next_n;
                 continue;
             }
+        }
+        if (cur_n % SUB_NODES == 0) {  // eight levels in one launch
+            node_hash_subtree_kernel<<<(unsigned)(cur_n / SUB_NODES), SUB_THREADS, 0, s>>>(cur, cur_n, pad_tab);
+            for (int l = 0; l < SUB_LEVELS; l++) {
+                cur += 32 * cur_n;
+                cur_n /= 2;
+            }
+            continue;
         }
         node_hash_kernel<<<(unsigned)((next_n + 255) / 256), 256, 0, s>>>(cur, next, cur_n, next_n, pad_tab);
         cur = next;

@@ -13,6 +13,7 @@ size_t merkle_node_count(size_t nleaves);
 int merkle_commit(const uint32_t* d_vals, int limbs, size_t n, const uint8_t* d_salts, uint8_t* d_nodes, cudaStream_t s);
 // Levels above the leaf digests (already in d_nodes[0 .. 32 n)).
 int merkle_upper_levels(uint8_t* d_nodes, size_t n, cudaStream_t s);
+int merkle_upper_launches(size_t n);  // how many kernels merkle_upper_levels(n) launches
 // Generic leaves: n byte strings of leaf_len bytes (any length), back to back (MerkleTree::new, src/merkle.rs:16-23).
 int merkle_build_bytes(const uint8_t* d_leaves, size_t n, size_t leaf_len, uint8_t* d_nodes, cudaStream_t s);
 // Gather the authentication path of `index` (src/merkle.rs:50-80) into d_path (depth * 32 bytes); pos bits on host.
