@@ -44,8 +44,12 @@ __global__ void __launch_bounds__(LDE::NT, 1) lde_expand_kernel(const LdeParams 
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
     {
-        uint2* tw_s = reinterpret_cast<uint2*>(smem + LDE::OFF_TW);
-        for (uint32_t i = tid; i < 4096u; i += LDE::NT) tw_s[i] = __ldg(&p.tw[i]);
+        uint2* tb = reinterpret_cast<uint2*>(smem + LDE::OFF_TB);
+        for (uint32_t i = tid; i < 15u * 512u; i += LDE::NT) {  // entry (2^t - 1 + kp, H = 32 a' + c) = omega_8192^((H + 512 kp) << (3 - t))
+            const uint32_t e = i >> 9, H = i & 511u;
+            const uint32_t t = (e >= 1u) + (e >= 3u) + (e >= 7u), kp = e - ((1u << t) - 1u);
+            tb[i] = __ldg(&p.tw[(H + 512u * kp) << (3u - t)]);
+        }
         uint2* ta = reinterpret_cast<uint2*>(smem + LDE::OFF_TA);
         for (uint32_t i = tid; i < 15u * 32u; i += LDE::NT) {  // entry (2^t - 1 + kp, c) = omega_8192^((16 c + 512 kp) << (3 - t))
             const uint32_t e = i >> 5, c = i & 31u;
@@ -106,7 +110,6 @@ __global__ void __launch_bounds__(LDE::NT, 1) lde_expand_kernel(const LdeParams 
     };
 
     uint4* tile_s = reinterpret_cast<uint4*>(smem + LDE::OFF_TILE);
-    const uint2* tw_s = reinterpret_cast<const uint2*>(smem + LDE::OFF_TW);
     if (tile < p.total_tiles) stage(fetch(tile), 0u);
     __syncthreads();
     while (tile < p.total_tiles) {
@@ -149,8 +152,8 @@ __global__ void __launch_bounds__(LDE::NT, 1) lde_expand_kernel(const LdeParams 
             // every warp holds its part of the tile in registers: the buffer is free for round A of the next tile, which a
             // warp starts as soon as its own stores below are issued — stores and arithmetic of neighbouring tiles overlap
             __syncthreads();
-            const uint32_t H = 32u * warp + lane;
-            lde_dit16(x, [&](int t, int kp) { return tw_s[(H + 512u * kp) << (3 - t)]; });
+            const uint2* tb = reinterpret_cast<const uint2*>(smem + LDE::OFF_TB) + 32u * warp + lane;  // H = 32 a' + c
+            lde_dit16(x, [&](int t, int kp) { return tb[512 * ((1 << t) - 1 + kp)]; });
             uint32_t* o = p.out + ((size_t)(4u * tile) << LDE::LOG_ROWS) + 32u * warp + lane;
 #pragma unroll
             for (int k = 0; k < 16; k++) {

@@ -22,8 +22,8 @@ struct LDE {
     static constexpr int NT = 512;
     static constexpr int LOG_ROWS = 13, LOG_COLS = 12;  // 8192 x 4096
     static constexpr uint32_t OFF_TILE = 0;                  // uint4 [16 a'][16 b][32 c]
-    static constexpr uint32_t OFF_TW = 131072;               // omega_8192^i, i < 4096
-    static constexpr uint32_t OFF_TA = OFF_TW + 4096 * 8;    // round-A twiddles [15][32 c]
+    static constexpr uint32_t OFF_TB = 131072;               // round-B twiddles [15][16 a'][32 c]: lanes read consecutive entries
+    static constexpr uint32_t OFF_TA = OFF_TB + 15 * 512 * 8;  // round-A twiddles [15][32 c]
     static constexpr uint32_t OFF_W32 = OFF_TA + 15 * 32 * 8;  // omega_32^c
     static constexpr uint32_t OFF_IN = OFF_W32 + 32 * 8;     // 2 x uint4 [512 rows]
     static constexpr uint32_t SMEM = OFF_IN + 2 * 512 * 16;
