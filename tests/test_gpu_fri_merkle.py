@@ -71,6 +71,52 @@ def test_cyclic_shards_fold_without_exchange(D):
         assert np.array_equal(D.to_host(part), full[r::G])
 
 
+@pytest.mark.parametrize("limbs", [1, 4])
+def test_fold_chain_in_one_call(D, limbs):
+    """bb_fri_fold_chain_shard_device: every fold of the prover's chain (src/fibonacci.rs:213-231 without the commits)
+    launched by one C call, on cyclic shards of 1, 2 and 8 ranks; every layer against the oracle."""
+    from toyni_b200 import multigpu as MG
+    log_m, shift = 13, 7
+    m = 1 << log_m
+    ee = O.random_field(limbs * m, seed=40 + limbs).reshape(m, 4) if limbs == 4 else O.random_field(m, seed=41)
+    betas = [[(3 * k + j + 5) % P for j in range(4)] if limbs == 4 else (3 * k + 5) % P for k in range(log_m)]
+    ref, xs, cur = [], O.domain_elements(m, shift), ee
+    while cur.shape[0] > 16:
+        cur = O.fri_fold_ext(cur, xs, betas[len(ref)]) if limbs == 4 else O.fri_fold(cur, xs, betas[len(ref)])
+        xs = (xs[: cur.shape[0]] * xs[: cur.shape[0]]) % np.uint64(P)
+        ref.append(cur)
+    for G in (1, 2, 8):
+        for r in range(G):
+            layers = MG.fold_chain_cuda(D.to_device(np.ascontiguousarray(ee[r::G])), log_m, shift, betas, r, G, until=16)
+            assert len(layers) == len(ref) + 1
+            for k, want in enumerate(ref):
+                assert np.array_equal(D.to_host(layers[k + 1]), want[r::G]), (G, r, k)
+
+
+def test_pool_allocations_and_device_copy(D):
+    """bb_pool_alloc / bb_pool_free / bb_pool_trim (stream-ordered, kept between uses) and bb_d2d, as the C++ prover uses
+    them: allocate, copy device to device both ways, free (NULL included), trim; the copies are exact."""
+    import ctypes as C
+    import torch
+    from toyni_b200.lib import check, lib
+    L = lib()
+    D._bind_stream()
+    x = D.to_device(O.random_field(1 << 16, seed=8))
+    p1, p2 = C.c_void_p(), C.c_void_p()
+    check(L.bb_pool_alloc(C.byref(p1), 4 << 16), "bb_pool_alloc")
+    check(L.bb_d2d(p1, C.c_void_p(x.data_ptr()), 4 << 16), "bb_d2d")
+    back = torch.empty_like(x)
+    check(L.bb_d2d(C.c_void_p(back.data_ptr()), p1, 4 << 16), "bb_d2d")
+    check(L.bb_sync(), "bb_sync")
+    assert torch.equal(back, x)
+    check(L.bb_pool_free(p1), "bb_pool_free")
+    check(L.bb_pool_alloc(C.byref(p2), 4 << 16), "bb_pool_alloc")
+    assert p2.value
+    check(L.bb_pool_free(p2), "bb_pool_free")
+    check(L.bb_pool_free(None), "bb_pool_free(NULL)")
+    check(L.bb_pool_trim(), "bb_pool_trim")
+
+
 def test_fold_host_mirror():
     from toyni_b200 import fri
     m = 1 << 10
@@ -83,9 +129,12 @@ def test_fold_host_mirror():
         fri.fri_fold(ev[:-1], xs, 1)
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 100, 1 << 10, (1 << 12) + 1])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 100, 255, 256, 257, 512, 1 << 10, (1 << 12) + 1, 1 << 14, 259 * 256, (1 << 18) + 256, 1 << 19])
 def test_merkle_commit_every_level(D, n):
-    """src/merkle.rs:25-48 with the prover's leaves (src/fibonacci.rs:340-363): every node of every level equal."""
+    """src/merkle.rs:25-48 with the prover's leaves (src/fibonacci.rs:340-363): every node of every level equal.  The sizes
+    walk every launch shape of merkle_upper_levels: single-CTA tail only (<= 256 nodes), one level per launch (sizes that
+    are not multiples of 256, odd levels duplicating their last node), eight levels per launch (multiples of 256, also a
+    non-power-of-two one), and the persistent large-level kernel (parents >= 2^18)."""
     import torch
     v = O.random_field(n, seed=n)
     salts = O.random_bytes(16 * n, seed=n + 1).reshape(n, 16)
