@@ -1,7 +1,7 @@
 // Micro-benchmark of the global-memory access shape of an NTT pass.  A 2^24-word array is seen as rows of 65536 words
 // (row stride 256 KB).  Every warp moves 8 KB units of (8 KB / W) rows x W bytes through its own shared-memory buffer
 // (cp.async in, STG.128 out), consecutive warps taking horizontally adjacent units, 16 warps per SM - the traffic of
-// ntt_pass_v5 without the arithmetic.  W = 32 B is the kernel's strip (256 rows); larger W shows what wider row
+// round 1's warp-private strip kernel (removed in round 2) without the arithmetic.  W = 32 B is the kernel's strip (256 rows); larger W shows what wider row
 // segments would buy; W = 8 KB is a plain streaming copy.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 tools/ubench_strided.cu -o tools/ubench_strided.bin
 #include <cstdio>
