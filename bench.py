@@ -558,8 +558,8 @@ def run_ours(args, rank, world, local_rank):
         pcie[name] = 8 * n / best / 1e9
     hv[:] = (np.arange(n, dtype=np.uint64) * np.uint64(7) + np.uint64(3)) % np.uint64(P)
     del dbuf
-    NTHR = 3
-    e2e_steps = max(NTHR * 2, min(args.steps, 24)) // NTHR * NTHR
+    NTHR = int(os.environ.get("TOYNI_E2E_THREADS", 3))
+    e2e_steps = max(NTHR * 2, min(args.steps, 96)) // NTHR * NTHR  # 32 per host thread: pipeline fill and drain are 1/32 of the run
     for _ in range(2):
         host_ntt.ntt_cuda(hv)
     barrier()
