@@ -447,6 +447,15 @@ int bb_fri_fold_chain_shard_device(const uint32_t* d_layer0, size_t m_local, uin
     while (m > until && m / 2 >= nranks) {
         if (folds >= nbetas) return note((int)cudaErrorInvalidValue);
         const size_t ml = m / nranks;
+        size_t left = 0;  // folds still to do from here
+        for (size_t mm = m; mm > until && mm / 2 >= nranks; mm /= 2) left++;
+        if (fri_fold_tail_applies(ml, left)) {  // the short end of the chain: one single-CTA launch
+            if (folds + left > nbetas) return note((int)cudaErrorInvalidValue);
+            CK(fri_fold_chain_tail(src, dst, ml, limbs, (int)log_m - (int)folds, x0, betas + folds * limbs, left, nranks, rank, s));
+            g_launches++;
+            folds += left;
+            break;
+        }
         CK(fri_fold_coset(src, dst, ml, limbs, (int)log_m - (int)folds, x0, betas + folds * limbs, nranks, rank, s));
         g_launches++;
         src = dst;

@@ -6,6 +6,8 @@
 // A general-xs form (arbitrary evaluation points, per-element Fermat inverse) keeps the reference signature.
 #include "fri_fold.cuh"
 
+#include <cstring>
+
 #include "merkle.cuh"
 #include "ntt_pass.cuh"
 #include "sha256.cuh"
@@ -197,6 +199,87 @@ int fri_fold_coset(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int li
         else
             fold_ext_kernel<PT, 0><<<blocks, 256, 0, s>>>((const uint4*)d_in, (uint4*)d_out, half, winv, fi, cm, sl, d_leaf_nodes);
     }
+    return (int)cudaGetLastError();
+}
+
+// The short end of a fold chain in ONE launch.  Below ~2^13 local values a fold is a few microseconds of launch and drain
+// around almost no work, and a 2^25 -> 16 chain has a dozen of them: a single CTA walks those layers with a block barrier
+// between them.  Layer f of the tail has evaluation points omega_M^(t << f) (M = the first tail layer's global size), so
+// one power table serves all layers; the per-fold constant beta_f / (2 x0_f) arrives as a kernel parameter.
+constexpr int FOLD_TAIL_MAX_FOLDS = 27, FOLD_TAIL_THREADS = 1024;
+constexpr size_t FOLD_TAIL_MAX_LOCAL = (size_t)1 << 13;
+struct FoldTailParams {
+    uint32_t nfolds, idx_mul, idx_add;
+    uint32_t c[FOLD_TAIL_MAX_FOLDS][16];  // limbs = 4: the ExtMat of the fold; limbs = 1: c[f][0] = Montgomery form of the constant
+};
+
+template <int LIMBS>
+__global__ void __launch_bounds__(FOLD_TAIL_THREADS) fold_tail_kernel(const uint32_t* in, uint32_t* out, size_t half, PowTable winv,
+                                                                      const FoldTailParams p) {
+    const uint32_t* src = in;
+    uint32_t* dst = out;
+    for (uint32_t f = 0; f < p.nfolds; f++) {
+        for (size_t i = threadIdx.x; i < half; i += FOLD_TAIL_THREADS) {
+            const uint32_t tw = pow_lookup(winv, ((uint32_t)i * p.idx_mul + p.idx_add) << f);  // omega_m^-i of this layer, Montgomery form
+            if (LIMBS == 1) {
+                const uint32_t a = __ldcg(src + i), b = __ldcg(src + i + half);  // L2: written by other threads of this CTA
+                dst[i] = add(halve(add(a, b)), monty_mul(sub(a, b), monty_mul(tw, p.c[f][0])));
+            } else {
+                const uint4 av = __ldcg(reinterpret_cast<const uint4*>(src) + i), bv = __ldcg(reinterpret_cast<const uint4*>(src) + i + half);
+                Ext a{{av.x, av.y, av.z, av.w}}, b{{bv.x, bv.y, bv.z, bv.w}};
+                Ext s = ext_add(a, b), d = ext_sub(a, b);
+#pragma unroll
+                for (int k = 0; k < 4; k++) d.c[k] = monty_mul(d.c[k], tw);
+                ExtMat cm;
+#pragma unroll
+                for (int k = 0; k < 16; k++) cm.m[k >> 2][k & 3] = p.c[f][k];
+                const Ext t = ext_mul_const(d, cm);
+                reinterpret_cast<uint4*>(dst)[i] =
+                    make_uint4(add(halve(s.c[0]), t.c[0]), add(halve(s.c[1]), t.c[1]), add(halve(s.c[2]), t.c[2]), add(halve(s.c[3]), t.c[3]));
+            }
+        }
+        __syncthreads();  // block-scope ordering of the stores above with the (L2) loads of the next layer
+        src = dst;
+        dst += half * LIMBS;
+        half /= 2;
+    }
+}
+
+static void fold_constant(uint32_t x0, const uint32_t* beta, int limbs, uint32_t out[16]) {
+    const uint32_t hx = bb::mul(HALF, bb::inv(x0));  // (1/2) * x0^-1
+    if (limbs == 1) {
+        out[0] = to_monty(bb::mul(hx, beta[0]));
+        return;
+    }
+    uint32_t c[4];
+    for (int k = 0; k < 4; k++) c[k] = bb::mul(hx, beta[k]);
+    for (int k = 0; k < 4; k++)
+        for (int j = 0; j < 4; j++) out[4 * k + j] = to_monty((k >= j) ? c[k - j] : bb::mul(EXT_W, c[k - j + 4]));
+}
+
+bool fri_fold_tail_applies(size_t m_local, size_t nfolds) { return m_local <= FOLD_TAIL_MAX_LOCAL && nfolds >= 2 && nfolds <= (size_t)FOLD_TAIL_MAX_FOLDS; }
+
+int fri_fold_chain_tail(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int limbs, int log_m_global, uint32_t x0,
+                        const uint32_t* betas, size_t nfolds, uint32_t idx_mul, uint32_t idx_add, cudaStream_t s) {
+    if (!fri_fold_tail_applies(m_local, nfolds) || (m_local >> nfolds) == 0 || (m_local & (m_local - 1)) || (limbs != 1 && limbs != 4) ||
+        log_m_global < 1 || log_m_global > MAX_LOG_N || x0 == 0)
+        return (int)cudaErrorInvalidValue;
+    PowTable winv;
+    int rc = engine_pow_table(bb::inv(root_of_unity(log_m_global)), log_m_global, 1u, &winv);
+    if (rc) return rc;
+    FoldTailParams p;
+    memset(&p, 0, sizeof p);
+    p.nfolds = (uint32_t)nfolds;
+    p.idx_mul = idx_mul;
+    p.idx_add = idx_add;
+    for (size_t f = 0; f < nfolds; f++) {
+        fold_constant(x0, betas + f * (size_t)limbs, limbs, p.c[f]);
+        x0 = bb::mul(x0, x0);
+    }
+    if (limbs == 1)
+        fold_tail_kernel<1><<<1, FOLD_TAIL_THREADS, 0, s>>>(d_in, d_out, m_local / 2, winv, p);
+    else
+        fold_tail_kernel<4><<<1, FOLD_TAIL_THREADS, 0, s>>>(d_in, d_out, m_local / 2, winv, p);
     return (int)cudaGetLastError();
 }
 

@@ -14,6 +14,11 @@ namespace bb {
 int fri_fold_coset(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int limbs, int log_m_global, uint32_t x0,
                    const uint32_t beta[4], uint32_t idx_mul, uint32_t idx_add, cudaStream_t s, int hash_mode = 0,
                    const uint8_t* d_salts = nullptr, uint8_t* d_leaf_nodes = nullptr);
+// The last `nfolds` folds of a chain in ONE single-CTA launch (layers of at most 2^13 local values): layer f reads the output
+// of layer f-1, x0 is squared from fold to fold, betas holds `limbs` values per fold, outputs land back to back in d_out.
+bool fri_fold_tail_applies(size_t m_local, size_t nfolds);
+int fri_fold_chain_tail(const uint32_t* d_in, uint32_t* d_out, size_t m_local, int limbs, int log_m_global, uint32_t x0,
+                        const uint32_t* betas, size_t nfolds, uint32_t idx_mul, uint32_t idx_add, cudaStream_t s);
 // Reference signature: arbitrary evaluation points xs[0..m/2) on the device.
 int fri_fold_xs(const uint32_t* d_in, const uint32_t* d_xs, uint32_t* d_out, size_t m, int limbs, const uint32_t beta[4],
                 cudaStream_t s);

@@ -314,36 +314,52 @@ class FourStepFused:
         self.mem.free()
 
 
+class FoldChain:
+    """A prepared FRI fold chain on one cyclic shard (global indices rank, rank+G, ...): layer sizes, the betas as a
+    C array and the output arena are set up once; `run(local)` is then ONE C call (bb_fri_fold_chain_shard_device)
+    that launches every fold back to back.  At eight ranks a 2^25 chain is ~60 us of kernels, so per-call Python
+    set-up (and, before that, a trip through Python per layer) was most of what the caller saw.
+    No communication while the layer has at least 2*world values."""
+
+    def __init__(self, log_m, shift, betas, rank, world, limbs, until=16, device="cuda"):
+        self.log_m, self.shift, self.rank, self.world, self.limbs, self.until = log_m, shift % P, rank, world, limbs, until
+        self.sizes, m = [], 1 << log_m
+        while m > until and (m // 2) >= world:
+            m //= 2
+            self.sizes.append(m // world)
+        self.m_local = (1 << log_m) // world
+        self.bt = np.ascontiguousarray(np.asarray([[int(v) % P for v in (b if limbs == 4 else [b])] for b in betas[:len(self.sizes)]],
+                                                  dtype=np.uint32).reshape(-1))
+        total = max(1, sum(self.sizes))
+        self.flat = torch.empty((total, 4) if limbs == 4 else (total,), dtype=torch.int32, device=device)
+
+    def run(self, local):
+        """local: this shard of layer 0.  Returns [local, layer 1, layer 2, ...] (views of the arena: valid until the
+        next run)."""
+        import ctypes as C
+
+        from .device import _bind_stream, _chk
+        from .lib import check, lib
+        assert local.shape[0] == self.m_local and (4 if local.dim() == 2 else 1) == self.limbs
+        if not self.sizes:
+            return [local]
+        _bind_stream()
+        folds = C.c_size_t(0)
+        check(lib().bb_fri_fold_chain_shard_device(_chk(local), self.m_local, self.log_m, self.shift, self.bt.ctypes.data, len(self.sizes),
+                                                   self.limbs, self.world, self.rank, self.until, _chk(self.flat), C.byref(folds)),
+              "bb_fri_fold_chain_shard_device")
+        assert folds.value == len(self.sizes)
+        layers, off = [local], 0
+        for s in self.sizes:
+            layers.append(self.flat[off:off + s])
+            off += s
+        return layers
+
+
 def fold_chain_cuda(local, log_m, shift, betas, rank, world, until=16):
-    """FRI fold chain on one cyclic shard (global indices rank, rank+G, ...), betas supplied up front.
-    Returns the list of local layers.  No communication while the layer has at least 2*world values.  One C call
-    (bb_fri_fold_chain_shard_device) launches every fold back to back: at eight ranks a layer lasts a few microseconds and
-    a per-layer trip through Python would be most of the chain."""
-    import ctypes as C
-
-    from .device import _bind_stream, _chk
-    from .lib import check, lib
-
-    _bind_stream()
-    limbs = 4 if local.dim() == 2 else 1
-    sizes, m = [], 1 << log_m
-    while m > until and (m // 2) >= world:
-        m //= 2
-        sizes.append(m // world)
-    if not sizes:
-        return [local]
-    bt = np.ascontiguousarray(np.asarray([[int(v) % P for v in (b if limbs == 4 else [b])] for b in betas[:len(sizes)]],
-                                         dtype=np.uint32).reshape(-1))
-    flat = torch.empty((sum(sizes), 4) if limbs == 4 else (sum(sizes),), dtype=torch.int32, device=local.device)
-    folds = C.c_size_t(0)
-    check(lib().bb_fri_fold_chain_shard_device(_chk(local), local.shape[0], log_m, shift % P, bt.ctypes.data, len(sizes), limbs, world, rank,
-                                               until, _chk(flat), C.byref(folds)), "bb_fri_fold_chain_shard_device")
-    assert folds.value == len(sizes)
-    layers, off = [local], 0
-    for s in sizes:
-        layers.append(flat[off:off + s])
-        off += s
-    return layers
+    """FRI fold chain on one cyclic shard, betas supplied up front: FoldChain prepared and run once.  Returns the list
+    of local layers (owning their arena)."""
+    return FoldChain(log_m, shift, betas, rank, world, 4 if local.dim() == 2 else 1, until, local.device).run(local)
 
 
 # ------------------------------------------------------------------ sharded FRI commit loop
