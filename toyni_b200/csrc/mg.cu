@@ -248,6 +248,15 @@ int bb_mg_fri_chain(void* mg, uint32_t log_m, uint32_t shift, int limbs, size_t 
         uint32_t* next = d_layers_out[r];
         // the fold partner i + m/2 is on the same device while m/2 >= G (cyclic layout): no exchange
         while (mm > final_size && (mm / 2) >= (size_t)G) {
+            size_t left = 0;  // folds still to do: the short end of the chain goes in one single-CTA launch
+            for (size_t t = mm; t > final_size && (t / 2) >= (size_t)G; t /= 2) left++;
+            if (fri_fold_tail_applies(mm / G, left)) {
+                MCK(fri_fold_chain_tail(cur, next, mm / G, limbs, (int)(log_m - k), x0, betas + (size_t)limbs * k, left, (uint32_t)G, (uint32_t)r,
+                                        m->stream[r]));
+                abi::count_launches(1);
+                k += (uint32_t)left;
+                break;
+            }
             MCK(fri_fold_coset(cur, next, mm / G, limbs, (int)(log_m - k), x0, betas + (size_t)limbs * k, (uint32_t)G, (uint32_t)r, m->stream[r]));
             abi::count_launches(1);
             cur = next;
