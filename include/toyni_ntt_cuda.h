@@ -269,6 +269,26 @@ int bb_mg_fri_chain(void* mg, uint32_t log_m, uint32_t shift, int limbs, size_t 
  * ntt_run_inplace does on one device, src/ntt.rs:108): scatter, four-step, gather.  Synchronous. */
 int bb_mg_ntt_host(void* mg, uint64_t* h_data, uint32_t log_n, int dir);
 
+/* ------------------------------------------------------------------------------------------
+ * 5. The prover loop behind one call: StarkProver::generate_proof (src/fibonacci.rs:99-310) for the Fibonacci AIR, every
+ *    LDE-sized array on the device, the Fiat-Shamir transcript (src/transcript.rs) on the host inside the library
+ *    (toyni_b200/host/toyni_prover.hpp is the loop).  The reference draws its randomness from thread_rng(); here it is an
+ *    argument, so that a proof is reproducible:
+ *      trace        trace_len canonical values (a power of two, 32 * trace_len <= 2^27)
+ *      mask         140 blinding coefficients (MASK_DEGREE, src/fibonacci.rs:19,117-120)
+ *      salts_trace, salts_quot   16 bytes per LDE point (32 * trace_len of them each)
+ *      salts_fri    toyni_fri_salt_bytes(trace_len) bytes: 16 per leaf of every salted FRI layer, layer 0 first
+ *      salts_on_device  non-zero: the three salt pointers are device pointers (nothing LDE-sized crosses PCIe)
+ *    The canonical proof bytes (the format of toyni_b200/proof.py / toyni::serialize_proof; the reference has no
+ *    serialization) are written to proof_out; *proof_len receives their length also when proof_cap is too small
+ *    (cudaErrorInvalidValue then).  toyni_prover_error() describes the last failure of this host thread.
+ * ---------------------------------------------------------------------------------------- */
+size_t toyni_fri_salt_bytes(size_t trace_len);
+int toyni_prove_fibonacci(const uint64_t* trace, size_t trace_len, const uint64_t* mask, const uint8_t* salts_trace,
+                          const uint8_t* salts_quot, const uint8_t* salts_fri, size_t salts_fri_bytes, int salts_on_device,
+                          uint8_t* proof_out, size_t proof_cap, size_t* proof_len);
+const char* toyni_prover_error(void);
+
 #ifdef __cplusplus
 }
 #endif

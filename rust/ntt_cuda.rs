@@ -72,6 +72,12 @@ mod cuda {
                                 challenge: Option<extern "C" fn(user: *mut c_void, root: *const u8, layer: u32, beta_out: *mut u32)>,
                                 user: *mut c_void, betas_in: *const u32, d_layers: *mut u32, d_nodes: *mut u8, roots_out: *mut u8,
                                 folds_out: *mut usize) -> CudaError;
+        // the whole prover loop behind one call (header section 5): canonical proof bytes out
+        fn toyni_fri_salt_bytes(trace_len: usize) -> usize;
+        fn toyni_prove_fibonacci(trace: *const u64, trace_len: usize, mask: *const u64, salts_trace: *const u8, salts_quot: *const u8,
+                                 salts_fri: *const u8, salts_fri_bytes: usize, salts_on_device: i32, proof_out: *mut u8, proof_cap: usize,
+                                 proof_len: *mut usize) -> CudaError;
+        fn toyni_prover_error() -> *const c_char;
         // one process, G devices (header section 4)
         fn bb_mg_init(ngpus: i32, mg_out: *mut *mut c_void) -> CudaError;
         fn bb_mg_destroy(mg: *mut c_void);

@@ -113,3 +113,41 @@ def test_gpu_proof_at_2_14_stays_on_the_device_and_verifies():
     assert F.verify(p, algebraic=True)
     for bad in _tamper_cases(p):
         assert not F.verify(bad, algebraic=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("trace_len", [64, 1 << 10])
+def test_one_call_prover_gives_the_oracle_proof_bytes(trace_len):
+    """toyni_prove_fibonacci (C ABI section 5: the whole loop of src/fibonacci.rs:99-310 behind one call, host salts) against
+    the oracle prover on the same randomness: identical canonical bytes; a wrong mask length is refused like the
+    reference's own length assumption."""
+    from toyni_b200 import prover
+    tr = F.fibonacci_trace(trace_len)
+    rnd = F.proof_randomness(trace_len)
+    ref = F.generate_proof(tr, *rnd, interpolate="intt")
+    blob = prover.generate_proof_native(tr, *rnd, as_bytes=True)
+    assert blob == F.serialize_proof(ref)
+    assert F.verify(prover.generate_proof_native(tr, *rnd))
+    with pytest.raises(AssertionError):
+        prover.generate_proof_native(tr, rnd[0][:-1], *rnd[1:])
+
+
+@pytest.mark.gpu
+def test_one_call_prover_with_device_salts_equals_the_python_loop():
+    """Same call with the salts resident on the device (trace 2^14): the bytes of the Python-driven loop over the same
+    device primitives, and a proof the restated verifier accepts."""
+    import torch
+    from oracle import oracle as O
+    from toyni_b200 import proof as product_proof
+    from toyni_b200 import prover
+    trace_len = 1 << 14
+    lde = trace_len * 32
+    tr = F.fibonacci_trace(trace_len)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(9)
+    salts = [torch.randint(0, 256, (m, 16), dtype=torch.uint8, device="cuda", generator=g) for m in (lde, lde, 2 * lde)]
+    mask = O.random_field(prover.MASK_DEGREE, 4)
+    a = prover.generate_proof_native(tr, mask, *salts, as_bytes=True)
+    b = product_proof.serialize_proof(prover.generate_proof(tr, mask, *salts))
+    assert a == b
+    assert F.verify(product_proof.deserialize_proof(a), algebraic=True)

@@ -12,9 +12,9 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "nvcc")
 EXTRA = os.environ.get("BB_NVCC_EXTRA", "").split()
 FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-diag-suppress", "186,128"]
+         "-Xcompiler", "-fPIC", "-diag-suppress", "186,128", "-I", os.path.join(HERE, "..", "include")]
 SOURCES = ["ntt_v7.cu", "ntt_v4_inst_d.cu", "ntt_v4_inst_c.cu", "ntt_v4_inst_b.cu", "ntt_v4_inst_a.cu", "ntt_inst_a.cu", "ntt_inst_b.cu", "ntt_inst_c.cu", "ntt_inst_d.cu", "ntt_dispatch.cu", "ntt_engine.cu",
-           "fri_fold.cu", "elementwise.cu", "prover_ew.cu", "merkle.cu", "c_abi.cu", "mg.cu"]
+           "fri_fold.cu", "elementwise.cu", "prover_ew.cu", "merkle.cu", "c_abi.cu", "mg.cu", "prover_abi.cu"]
 SO = os.path.join(HERE, "libntt_cuda.so")
 AR = os.path.join(HERE, "libntt_cuda.a")
 

@@ -20,7 +20,9 @@
 
 #include "toyni_ntt_cuda.h"
 
-extern "C" int cudaGetDeviceCount(int*);  // libcudart, as src/ntt.rs:102
+#if !defined(__CUDACC__) && !defined(__CUDA_RUNTIME_H__)
+extern "C" int cudaGetDeviceCount(int*);  // libcudart, as src/ntt.rs:102 (a plain C++ host needs no CUDA headers)
+#endif
 
 namespace toyni {
 

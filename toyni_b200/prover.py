@@ -108,6 +108,49 @@ def _as_salts(s, device):
     return torch.from_numpy(np.ascontiguousarray(s, np.uint8).reshape(-1, 16)).to(device)
 
 
+def generate_proof_native(trace_column, mask, salts_trace, salts_quot, salts_fri, device="cuda", as_bytes=False):
+    """The same proof from ONE call into the library (toyni_prove_fibonacci: the loop of toyni_prover.hpp, compiled host
+    code, transcript included) — no Python between the stages.  Salts may be numpy arrays (copied by the library) or CUDA
+    uint8 tensors (used in place).  Returns the proof dict of generate_proof, or its canonical bytes."""
+    import ctypes as C
+
+    from .lib import check, lib
+    from .proof import deserialize_proof
+    D._bind_stream()
+    trace = np.ascontiguousarray(np.asarray(trace_column, dtype=np.uint64))
+    mask = np.ascontiguousarray(np.asarray(mask, dtype=np.uint64).reshape(-1))
+    assert mask.size == MASK_DEGREE, f"mask: {mask.size} coefficients given, {MASK_DEGREE} required"
+    L = lib()
+    need = L.toyni_fri_salt_bytes(trace.size)
+    on_dev = all(isinstance(s, torch.Tensor) and s.is_cuda for s in (salts_trace, salts_quot, salts_fri))
+    if on_dev:
+        keep = [s.contiguous().view(torch.uint8).reshape(-1) for s in (salts_trace, salts_quot, salts_fri)]
+        ptrs = [C.c_void_p(k.data_ptr()) for k in keep]
+        nfri = keep[2].numel()
+    else:
+        keep = [np.ascontiguousarray(s.cpu().numpy() if isinstance(s, torch.Tensor) else s, dtype=np.uint8).reshape(-1)
+                for s in (salts_trace, salts_quot, salts_fri)]
+        ptrs = [C.c_void_p(k.ctypes.data) for k in keep]
+        nfri = keep[2].size
+    lde = trace.size * BLOWUP
+    assert (keep[0].numel() if on_dev else keep[0].size) == 16 * lde and (keep[1].numel() if on_dev else keep[1].size) == 16 * lde
+    assert nfri >= need, f"salts_fri: {nfri} bytes given, {need} needed"
+    cap = 4 << 20
+    while True:
+        out = np.empty(cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        rc = L.toyni_prove_fibonacci(trace.ctypes.data, trace.size, mask.ctypes.data, ptrs[0], ptrs[1], ptrs[2], nfri, 1 if on_dev else 0,
+                                     out.ctypes.data, cap, C.byref(n))
+        if rc and n.value > cap:  # cannot happen below 2^27 LDE points; kept for safety
+            cap = n.value
+            continue
+        if rc:
+            raise RuntimeError(f"toyni_prove_fibonacci: {L.toyni_prover_error().decode()} (code {rc})")
+        break
+    data = out[:n.value].tobytes()
+    return data if as_bytes else deserialize_proof(data)
+
+
 def generate_proof(trace_column, mask, salts_trace, salts_quot, salts_fri, device="cuda", timings=None):
     """Every array of LDE size stays on the device: LDE, constraint / quotient / DEEP formulas, commits, FRI commit
     loop and openings.  Salts may be numpy arrays or CUDA uint8 tensors.  `timings` (a dict) receives the wall time
