@@ -154,7 +154,7 @@ def test_columns_64_x_2_22(D):
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("n_coeffs,shift", [((1 << 20) + 140, 7), (12345, 7), (1 << 21, 7), (1 << 20, 1), ((1 << 21) - 4097, 3)])
+@pytest.mark.parametrize("n_coeffs,shift", [((1 << 20) + 140, 7), (12345, 7), (1 << 21, 7), (1 << 20, 1), ((1 << 21) - 4097, 3), (1, 7), (4097, 5)])
 def test_lde_to_2_25_ragged_inputs(D, oracle_threads, n_coeffs, shift):
     """The blowup-32 plan (expansion pass + TMA-staged pass 2) on the inputs it must cope with: the masked trace polynomial
     of a 2^20-row proof (2^20 + 140 coefficients, src/fibonacci.rs:117-121), short and ragged coefficient vectors, twice the

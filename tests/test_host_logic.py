@@ -245,3 +245,17 @@ def test_tma_kernel_index_model_is_a_dft():
     assert np.array_equal(got, O.ntt(x))
     back = np.array([int(v) for v in m.two_pass_ntt([int(v) for v in got], g, inverse=True)], dtype=np.uint64)
     assert np.array_equal(back, x)
+
+
+def test_lde_expansion_pass_index_model():
+    """tools/lde_model.py restates the index logic of lde_expand_kernel (two radix-16 DIT rounds whose butterfly twiddles
+    carry the coset factors, table of w_8192 powers below 4096 only, rows >= 256 folded in with w_32^c) on the CPU: one
+    column of Z[j][k1] against the direct sum, for 2^20 coefficients (256 rows) and the masked trace polynomial (257)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("lde_model", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "lde_model.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rng = np.random.default_rng(7)
+    for nrows in (256, 257, 3):
+        m.check(nrows, rng, extra=6)

@@ -63,12 +63,17 @@ def column(xp, nrows):
     return Z
 
 
-rng = np.random.default_rng(1)
-for nrows in (256, 257, 300, 512, 100):
+def check(nrows, rng, extra=20):
     xp = [int(v) for v in rng.integers(0, P, nrows)]
     got = column(xp, nrows)
-    ks = [0, 1, 31, 32, 33, 511, 512, 4095, 4096, 8191] + [int(v) for v in rng.integers(0, 8192, 20)]
+    ks = [0, 1, 31, 32, 33, 511, 512, 4095, 4096, 8191] + [int(v) for v in rng.integers(0, 8192, extra)]
     for k1 in ks:
         want = sum(xp[i1] * pow(W, i1 * k1, P) for i1 in range(nrows)) % P
         assert got[k1] == want, (nrows, k1)
-    print("nrows", nrows, "ok")
+
+
+if __name__ == "__main__":
+    rng = np.random.default_rng(1)
+    for nrows in (256, 257, 300, 512, 100):
+        check(nrows, rng)
+        print("nrows", nrows, "ok")
