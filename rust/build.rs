@@ -33,7 +33,7 @@ fn main() {
     assert!(ok, "feature `cuda` needs nvcc (CUDA >= 12.8 for sm_100a)");
 
     let out_dir = PathBuf::from(env::var("OUT_DIR").unwrap());
-    let src_dir = PathBuf::from("cuda"); // toyni_b200/csrc + include/ of this repository copied to cuda/
+    let src_dir = PathBuf::from("cuda"); // toyni_b200/csrc/*, toyni_b200/host/*.hpp and include/*.h of this repository, flat
     let mut objects = Vec::new();
     for src in sources(&src_dir).iter() {
         let obj = out_dir.join(src.replace(".cu", ".o"));

@@ -1,5 +1,9 @@
 // C ABI of the library (include/toyni_ntt_cuda.h).  Section numbers follow the header.
+#if __has_include("toyni_ntt_cuda.h")
+#include "toyni_ntt_cuda.h"  // -I include (build.py) or the flat cuda/ directory of the toyni tree
+#else
 #include "../../include/toyni_ntt_cuda.h"
+#endif
 
 #include <atomic>
 #include <cstdio>

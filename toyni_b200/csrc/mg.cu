@@ -2,7 +2,11 @@
 // Nothing like this exists in the reference (single device, default stream).  Peer access is enabled between all
 // pairs, so a kernel on GPU q stores straight into a buffer of GPU r (NVLink / NVSwitch); ordering between devices is
 // CUDA events on per-device streams — no NCCL, no IPC handles, no host synchronisation inside a transform.
+#if __has_include("toyni_ntt_cuda.h")
+#include "toyni_ntt_cuda.h"  // -I include (build.py) or the flat cuda/ directory of the toyni tree
+#else
 #include "../../include/toyni_ntt_cuda.h"
+#endif
 
 #include <cstring>
 #include <vector>

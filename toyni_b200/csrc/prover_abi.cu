@@ -2,7 +2,11 @@
 // (toyni_b200/host/toyni_prover.hpp: StarkProver::generate_proof of src/fibonacci.rs:99-310 over the device entry points
 // of this library, transcript on the host); this file only gives it a C face so that a host in any language — the Rust
 // crate, Python through ctypes — gets a serialized proof without a per-stage trip through its own runtime.
+#if __has_include("toyni_ntt_cuda.h")
+#include "toyni_ntt_cuda.h"  // -I include (build.py) or the flat cuda/ directory of the toyni tree
+#else
 #include "../../include/toyni_ntt_cuda.h"
+#endif
 
 #if __has_include("toyni_prover.hpp")
 #include "toyni_prover.hpp"  // flat layout: cuda/ of the toyni tree
