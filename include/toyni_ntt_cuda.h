@@ -189,6 +189,20 @@ int bb_fri_commit_device(const uint32_t* d_layer0, size_t n, uint32_t shift, siz
 int bb_merkle_open_batch_device(const uint8_t* d_nodes, size_t nleaves, const uint64_t* indices, size_t nq, uint8_t* paths_out,
                                 uint8_t* pos_out, size_t* depth_out);
 int bb_gather_device(const void* d_src, size_t elem_bytes, const uint64_t* indices, size_t nq, void* out);
+/* The openings of a whole proof in ONE launch, one copy and one synchronisation: request r opens leaves
+ * indices[first .. first + count) of its own tree (requests cover indices[0 .. nq) in order).  paths_out receives, query
+ * after query, depth(tree) * 32 bytes (paths_bytes = their total, checked), pos_out the matching position flags,
+ * vals_out nq * elem_bytes bytes (elem_bytes = 4 for base-field leaves, 16 for Ext), salts_out nq * 16 bytes (zeros for
+ * unsalted trees).  A 2^20-row proof has 24 trees and ~2100 openings: 72 round trips through the per-tree calls. */
+typedef struct {
+    const uint8_t* d_nodes; /* every level of the tree, leaf level first (bb_merkle_commit_device) */
+    size_t nleaves;
+    const void* d_vals;     /* the committed values */
+    const uint8_t* d_salts; /* 16 bytes per leaf, NULL for an unsalted tree */
+    size_t first, count;
+} bb_open_request;
+int bb_merkle_open_multi_device(const bb_open_request* reqs, size_t nreq, const uint64_t* indices, size_t nq, size_t elem_bytes,
+                                uint8_t* paths_out, size_t paths_bytes, uint8_t* pos_out, uint8_t* vals_out, uint8_t* salts_out);
 
 /* Re-layout after the cyclic -> block exchange of the sharded FRI commit (one process per GPU): d_src holds `groups`
  * runs of `chunk` elements (limbs = 1 or 4 words each), run r supplying destination positions r, r + groups, ... */

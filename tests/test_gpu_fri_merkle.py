@@ -267,3 +267,53 @@ def test_fold_chain_2_25_to_16_constant_final_layer(D):
     assert len(layers) == 22 and layers[-1].shape[0] == 16
     last = layers[-1]
     assert bool((last == last[0]).all())
+
+
+def test_openings_of_several_trees_in_one_call(D):
+    """bb_merkle_open_multi_device (the openings of a whole proof in one launch) against the per-tree calls
+    (bb_merkle_open_batch_device + bb_gather_device, themselves checked against src/merkle.rs:50-80 in the oracle): an odd
+    salted tree, a power-of-two unsalted one and a single-leaf tree; paths, position flags, values and salts."""
+    import ctypes as C
+    import torch
+    from toyni_b200.lib import check, lib
+    L = lib()
+
+    class Req(C.Structure):
+        _fields_ = [("d_nodes", C.c_void_p), ("nleaves", C.c_size_t), ("d_vals", C.c_void_p), ("d_salts", C.c_void_p),
+                    ("first", C.c_size_t), ("count", C.c_size_t)]
+
+    specs = [(1000, True, [0, 999, 998, 501, 7]), (64, False, [63, 0, 31]), (1, False, [0])]
+    trees, reqs, indices = [], [], []
+    for n, salted, idx in specs:
+        v = D.to_device(O.random_field(n, seed=n + 5))
+        s = torch.from_numpy(O.random_bytes(16 * n, seed=n + 6).reshape(n, 16)).cuda() if salted else None
+        nodes, _ = D.merkle_commit(v, s)
+        trees.append((v, s, nodes))
+        reqs.append(Req(nodes.data_ptr(), n, v.data_ptr(), s.data_ptr() if salted else None, len(indices), len(idx)))
+        indices += idx
+    depths = [max(n - 1, 0).bit_length() for n, _, _ in specs]
+    nq = len(indices)
+    pbytes = sum(32 * d * len(idx) for d, (_, _, idx) in zip(depths, specs))
+    paths = np.zeros(max(pbytes, 1), np.uint8)
+    pos = np.zeros(max(pbytes // 32, 1), np.uint8)
+    vals = np.zeros(nq, np.uint32)
+    salts = np.zeros((nq, 16), np.uint8)
+    ia = np.asarray(indices, np.uint64)
+    D._bind_stream()
+    check(L.bb_merkle_open_multi_device((Req * len(reqs))(*reqs), len(reqs), ia.ctypes.data, nq, 4, paths.ctypes.data, pbytes,
+                                        pos.ctypes.data, vals.ctypes.data, salts.ctypes.data), "bb_merkle_open_multi_device")
+    po = q = 0
+    for (n, salted, idx), d, (v, s, nodes) in zip(specs, depths, trees):
+        want_paths, want_pos = D.merkle_open_batch(nodes, n, idx)
+        want_vals = D.gather(v, idx).view(np.uint32).reshape(-1)
+        for k in range(len(idx)):
+            assert np.array_equal(paths[32 * po:32 * (po + d)].reshape(d, 32), want_paths[k])
+            assert np.array_equal(pos[po:po + d], want_pos[k])
+            assert vals[q] == want_vals[k]
+            assert np.array_equal(salts[q], D.gather(s, [idx[k]])[0] if salted else np.zeros(16, np.uint8))
+            po += d
+            q += 1
+    # a request list that does not cover the indices, or a wrong paths size, is refused
+    assert L.bb_merkle_open_multi_device((Req * 1)(reqs[0]), 1, ia.ctypes.data, nq, 4, paths.ctypes.data, pbytes, pos.ctypes.data,
+                                         vals.ctypes.data, salts.ctypes.data) != 0
+    L.bb_clear_error()

@@ -527,6 +527,8 @@ struct SmallScratch {
     int dev = -1;
 };
 thread_local SmallScratch g_small[64][2];  // per host thread and device
+static thread_local std::vector<uint8_t> g_open_host;  // host landing buffer of bb_merkle_open_multi_device
+
 int small_scratch(int slot, size_t bytes, void** out) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -579,6 +581,57 @@ int bb_merkle_open_batch_device(const uint8_t* d_nodes, size_t nleaves, const ui
         rc = (int)cudaMemcpyAsync(paths_out, d_paths, nq * depth * 32, cudaMemcpyDeviceToHost, s);
     }
     if (rc == 0) rc = (int)cudaStreamSynchronize(s);
+    return note(rc);
+}
+int bb_merkle_open_multi_device(const bb_open_request* reqs, size_t nreq, const uint64_t* indices, size_t nq, size_t elem_bytes,
+                                uint8_t* paths_out, size_t paths_bytes, uint8_t* pos_out, uint8_t* vals_out, uint8_t* salts_out) {
+    if (!reqs || !indices || !paths_out || !pos_out || !vals_out || !salts_out || elem_bytes == 0 || elem_bytes > 32)
+        return note((int)cudaErrorInvalidValue);
+    if (nq == 0) return 0;
+    std::vector<OpenQuery> qs(nq);
+    size_t path_off = 0, flags = 0, covered = 0;
+    for (size_t r = 0; r < nreq; r++) {
+        const bb_open_request& t = reqs[r];
+        if (t.first != covered || t.first + t.count > nq || !t.d_nodes || !t.d_vals) return note((int)cudaErrorInvalidValue);
+        size_t depth = 0;
+        for (size_t m = t.nleaves; m > 1; m = (m + 1) / 2) depth++;
+        for (size_t k = 0; k < t.count; k++) {
+            const size_t q = t.first + k;
+            if (indices[q] >= t.nleaves) return note((int)cudaErrorInvalidValue);
+            qs[q] = OpenQuery{t.d_nodes, (const uint8_t*)t.d_vals, t.d_salts, t.nleaves, indices[q], path_off};
+            size_t level_n = t.nleaves, cur = (size_t)indices[q];
+            while (level_n > 1) {  // position flags need no device data (src/merkle.rs:67-73)
+                const size_t sib = (cur % 2 == 0) ? cur + 1 : cur - 1;
+                pos_out[flags++] = (sib >= level_n) ? 1 : (uint8_t)(cur % 2 == 1);
+                cur /= 2;
+                level_n = (level_n + 1) / 2;
+            }
+            path_off += depth * 32;
+        }
+        covered += t.count;
+    }
+    if (covered != nq || path_off != paths_bytes) return note((int)cudaErrorInvalidValue);
+    // one device buffer [queries][paths][values][salts], one upload, one launch, one download, one synchronisation
+    cudaStream_t s = cur_stream();
+    const size_t qbytes = (nq * sizeof(OpenQuery) + 31) & ~(size_t)31, pbytes = (paths_bytes + 31) & ~(size_t)31;
+    const size_t vbytes = (nq * elem_bytes + 31) & ~(size_t)31;
+    uint8_t *d_q = nullptr, *d_out = nullptr;
+    CK(small_scratch(0, qbytes, (void**)&d_q));
+    CK(small_scratch(1, pbytes + vbytes + nq * 16, (void**)&d_out));
+    int rc = (int)cudaMemcpyAsync(d_q, qs.data(), nq * sizeof(OpenQuery), cudaMemcpyHostToDevice, s);
+    if (rc == 0) rc = merkle_open_multi((const OpenQuery*)d_q, nq, (uint32_t)elem_bytes, d_out, d_out + pbytes, d_out + pbytes + vbytes, s);
+    if (rc == 0) {
+        g_launches++;
+        std::vector<uint8_t>& h = g_open_host;
+        h.resize(pbytes + vbytes + nq * 16);
+        rc = (int)cudaMemcpyAsync(h.data(), d_out, h.size(), cudaMemcpyDeviceToHost, s);
+        if (rc == 0) rc = (int)cudaStreamSynchronize(s);
+        if (rc == 0) {
+            memcpy(paths_out, h.data(), paths_bytes);
+            memcpy(vals_out, h.data() + pbytes, nq * elem_bytes);
+            memcpy(salts_out, h.data() + pbytes + vbytes, nq * 16);
+        }
+    }
     return note(rc);
 }
 int bb_gather_device(const void* d_src, size_t elem_bytes, const uint64_t* indices, size_t nq, void* out) {

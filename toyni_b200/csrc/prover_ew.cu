@@ -116,6 +116,25 @@ __global__ void gather_elems_kernel(const uint8_t* __restrict__ src, uint32_t el
         out[(size_t)blockIdx.x * elem_bytes + b] = src[(size_t)idx[blockIdx.x] * elem_bytes + b];
 }
 
+// The openings of a whole proof in one launch: one block per query, each with its own tree (src/fibonacci.rs:250-295 over
+// src/merkle.rs:59-77).  The block copies the sibling digests level by level, then the opened value and its salt.
+__global__ void __launch_bounds__(32) open_multi_kernel(const OpenQuery* __restrict__ qs, uint32_t val_bytes, uint8_t* __restrict__ paths,
+                                                        uint8_t* __restrict__ vals, uint8_t* __restrict__ salts) {
+    const OpenQuery q = qs[blockIdx.x];
+    size_t level_off = 0, level_n = q.nleaves, cur = q.index;
+    uint8_t* dst = paths + q.path_off;
+    for (uint32_t d = 0; level_n > 1; d++) {
+        const size_t sib = (cur % 2 == 0) ? cur + 1 : cur - 1;
+        const size_t src = (sib >= level_n) ? cur : sib;
+        dst[32 * d + threadIdx.x] = q.nodes[32 * (level_off + src) + threadIdx.x];
+        cur /= 2;
+        level_off += level_n;
+        level_n = (level_n + 1) / 2;
+    }
+    if (threadIdx.x < val_bytes) vals[(size_t)blockIdx.x * val_bytes + threadIdx.x] = q.vals[q.index * val_bytes + threadIdx.x];
+    if (threadIdx.x < 16u) salts[(size_t)blockIdx.x * 16 + threadIdx.x] = q.salts ? q.salts[q.index * 16 + threadIdx.x] : (uint8_t)0;
+}
+
 // dst[(j*G + r)] = src[r*c + j], elements of `limbs` words (re-layout after the cyclic -> block exchange)
 __global__ void __launch_bounds__(256) interleave_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t groups,
                                                          size_t chunk, uint32_t limbs) {
@@ -179,6 +198,12 @@ int poly_eval(const uint32_t* d_c, size_t n, uint32_t z, unsigned long long* d_a
 int merkle_gather_paths(const uint8_t* d_nodes, size_t nleaves, const unsigned long long* d_idx, size_t nq, uint32_t depth, uint8_t* d_paths,
                         cudaStream_t s) {
     if (nq && depth) gather_paths_kernel<<<(unsigned)nq, 32, 0, s>>>(d_nodes, nleaves, d_idx, depth, d_paths);
+    return (int)cudaGetLastError();
+}
+int merkle_open_multi(const OpenQuery* d_queries, size_t nq, uint32_t val_bytes, uint8_t* d_paths, uint8_t* d_vals, uint8_t* d_salts,
+                      cudaStream_t s) {
+    if (val_bytes == 0 || val_bytes > 32) return (int)cudaErrorInvalidValue;
+    if (nq) open_multi_kernel<<<(unsigned)nq, 32, 0, s>>>(d_queries, val_bytes, d_paths, d_vals, d_salts);
     return (int)cudaGetLastError();
 }
 int gather_elems(const void* d_src, uint32_t elem_bytes, const unsigned long long* d_idx, size_t nq, void* d_out, cudaStream_t s) {

@@ -19,6 +19,16 @@ int poly_eval(const uint32_t* d_c, size_t n, uint32_t z, unsigned long long* d_a
 int merkle_gather_paths(const uint8_t* d_nodes, size_t nleaves, const unsigned long long* d_idx, size_t nq, uint32_t depth, uint8_t* d_paths,
                         cudaStream_t s);
 int gather_elems(const void* d_src, uint32_t elem_bytes, const unsigned long long* d_idx, size_t nq, void* d_out, cudaStream_t s);
+// one query of merkle_open_multi: tree, opened index, where its path goes (byte offset), leaf value and salt arrays
+struct OpenQuery {
+    const uint8_t* nodes;
+    const uint8_t* vals;
+    const uint8_t* salts;  // nullptr: unsalted tree
+    unsigned long long nleaves, index, path_off;
+};
+// paths, values (val_bytes each) and salts (16 bytes, zero for unsalted trees) of nq queries over any number of trees
+int merkle_open_multi(const OpenQuery* d_queries, size_t nq, uint32_t val_bytes, uint8_t* d_paths, uint8_t* d_vals, uint8_t* d_salts,
+                      cudaStream_t s);
 // dst[j*G + r] = src[r*chunk + j]: G runs of `chunk` elements (limbs words each) interleaved
 int interleave(const uint32_t* d_src, uint32_t* d_dst, uint32_t groups, size_t chunk, uint32_t limbs, cudaStream_t s);
 }  // namespace bb

@@ -162,6 +162,62 @@ struct DeviceTree {
     }
 };
 
+/// The openings of many trees in one call (bb_merkle_open_multi_device): add(tree, indices) per tree, run() returns the
+/// openings tree by tree, in the order they were added.
+class OpeningBatch {
+  public:
+    void add(const DeviceTree& t, const std::vector<uint64_t>& idx) {
+        bb_open_request r;
+        r.d_nodes = t.nodes;
+        r.nleaves = t.n;
+        r.d_vals = t.vals;
+        r.d_salts = t.salts;
+        r.first = indices_.size();
+        r.count = idx.size();
+        reqs_.push_back(r);
+        indices_.insert(indices_.end(), idx.begin(), idx.end());
+    }
+    std::vector<std::vector<MerkleOpening>> run() const {
+        const size_t nq = indices_.size();
+        size_t path_bytes = 0;
+        std::vector<size_t> depth(reqs_.size());
+        for (size_t r = 0; r < reqs_.size(); r++) {
+            size_t d = 0;
+            while ((size_t(1) << d) < reqs_[r].nleaves) d++;
+            depth[r] = d;
+            path_bytes += reqs_[r].count * d * 32;
+        }
+        std::vector<uint8_t> paths(path_bytes + 1), pos(path_bytes / 32 + 1), salts(16 * nq + 1);
+        std::vector<uint32_t> vals(nq + 1);
+        check(bb_merkle_open_multi_device(reqs_.data(), reqs_.size(), indices_.data(), nq, 4, paths.data(), path_bytes, pos.data(),
+                                          reinterpret_cast<uint8_t*>(vals.data()), salts.data()),
+              "bb_merkle_open_multi_device");
+        std::vector<std::vector<MerkleOpening>> out(reqs_.size());
+        size_t po = 0;  // digests consumed so far
+        for (size_t r = 0; r < reqs_.size(); r++) {
+            out[r].resize(reqs_[r].count);
+            for (size_t k = 0; k < reqs_[r].count; k++) {
+                const size_t q = reqs_[r].first + k;
+                MerkleOpening& o = out[r][k];
+                o.index = indices_[q];
+                o.value = BabyBear{vals[q]};
+                if (reqs_[r].d_salts) o.salt.assign(salts.begin() + 16 * q, salts.begin() + 16 * (q + 1));
+                o.path.resize(depth[r]);
+                o.position.resize(depth[r]);
+                for (size_t d = 0; d < depth[r]; d++, po++) {
+                    std::memcpy(o.path[d].data(), &paths[32 * po], 32);
+                    o.position[d] = pos[po] != 0;
+                }
+            }
+        }
+        return out;
+    }
+
+  private:
+    std::vector<bb_open_request> reqs_;
+    std::vector<uint64_t> indices_;
+};
+
 }  // namespace detail
 
 /// src/transcript.rs: state = label, absorb appends, squeeze hashes the state and replaces it with the digest.
@@ -408,21 +464,38 @@ class StarkProver {
 
         mark("DEEP + FRI commit loop");
 
-        // 7. query phase (:250-295): one batched opening per tree
+        // 7. query phase (:250-295): every opening of the proof — 24 trees, ~2100 leaves at 2^20 rows — in ONE launch, one
+        //    copy and one synchronisation (bb_merkle_open_multi_device)
         const std::vector<uint64_t> queries = tr.squeeze_indices(NUM_QUERIES, lde / 2);
         const DeviceTree trace_tree{d_tlde.get(), d_nodes_t.get(), d_salts_trace, lde};
         const DeviceTree quot_tree{d_q.get(), d_nodes_q.get(), d_salts_quot, lde};
-        std::vector<uint64_t> idx;
-        for (uint64_t q : queries) {
-            idx.push_back(q);
-            idx.push_back(q + lde / 2);
+        OpeningBatch batch;
+        {
+            std::vector<uint64_t> idx;
+            for (uint64_t q : queries) {
+                idx.push_back(q);
+                idx.push_back(q + lde / 2);
+            }
+            batch.add(trees[0], idx);
+            idx.clear();
+            for (uint64_t q : queries)
+                for (uint64_t k = 0; k < 3; k++) idx.push_back((q + k * BLOWUP) % lde);
+            batch.add(trace_tree, idx);
+            batch.add(quot_tree, queries);
+            std::vector<uint64_t> cur = queries;
+            for (size_t k = 1; k + 1 < trees.size(); k++) {  // :270-283
+                const uint64_t half = trees[k].n / 2;
+                idx.clear();
+                for (uint64_t& i : cur) {
+                    i %= half;
+                    idx.push_back(i);
+                    idx.push_back(i + half);
+                }
+                batch.add(trees[k], idx);
+            }
         }
-        std::vector<MerkleOpening> deep = trees[0].open_many(idx);
-        idx.clear();
-        for (uint64_t q : queries)
-            for (uint64_t k = 0; k < 3; k++) idx.push_back((q + k * BLOWUP) % lde);
-        std::vector<MerkleOpening> trc = trace_tree.open_many(idx);
-        std::vector<MerkleOpening> quo = quot_tree.open_many(queries);
+        std::vector<std::vector<MerkleOpening>> opened = batch.run();
+        std::vector<MerkleOpening>&deep = opened[0], &trc = opened[1], &quo = opened[2];
         proof.query_proofs.resize(NUM_QUERIES);
         for (size_t n = 0; n < NUM_QUERIES; n++) {
             QueryProof& qp = proof.query_proofs[n];
@@ -433,19 +506,7 @@ class StarkProver {
             qp.trace_opening_g = std::move(trc[3 * n + 1]);
             qp.trace_opening_gg = std::move(trc[3 * n + 2]);
             qp.quotient_opening = std::move(quo[n]);
-        }
-        std::vector<uint64_t> cur = queries;
-        for (size_t k = 1; k + 1 < trees.size(); k++) {  // :270-283
-            const uint64_t half = trees[k].n / 2;
-            idx.clear();
-            for (uint64_t& i : cur) {
-                i %= half;
-                idx.push_back(i);
-                idx.push_back(i + half);
-            }
-            std::vector<MerkleOpening> f = trees[k].open_many(idx);
-            for (size_t n = 0; n < NUM_QUERIES; n++)
-                proof.query_proofs[n].fri_openings.emplace_back(std::move(f[2 * n]), std::move(f[2 * n + 1]));
+            for (size_t k = 3; k < opened.size(); k++) qp.fri_openings.emplace_back(std::move(opened[k][2 * n]), std::move(opened[k][2 * n + 1]));
         }
         std::vector<uint32_t> fin(sizes.back());
         check(bb_d2h(fin.data(), trees.back().vals, fin.size() * 4), "bb_d2h");

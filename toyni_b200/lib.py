@@ -42,6 +42,8 @@ _SIGNATURES = {
     "toyni_prove_fibonacci": ([C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                C.c_size_t, C.POINTER(C.c_size_t)], C.c_int),
     "toyni_prover_error": ([], C.c_char_p),
+    "bb_merkle_open_multi_device": ([C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                     C.c_void_p], C.c_int),
     "bb_pool_alloc": ([C.POINTER(C.c_void_p), C.c_size_t], C.c_int),
     "bb_pool_free": ([C.c_void_p], C.c_int),
     "bb_pool_trim": ([], C.c_int),
