@@ -20,6 +20,17 @@ mod cuda {
     type CudaError = i32;
     const CUDA_SUCCESS: CudaError = 0;
 
+    /// bb_open_request of the header: one tree and the slice of the index list that opens it
+    #[repr(C)]
+    pub struct OpenRequest {
+        pub d_nodes: *const u8,
+        pub nleaves: usize,
+        pub d_vals: *const c_void,
+        pub d_salts: *const u8, // null: unsalted tree
+        pub first: usize,
+        pub count: usize,
+    }
+
     #[link(name = "ntt_cuda", kind = "static")]
     unsafe extern "C" {
         // unchanged from the reference (src/ntt.rs:96-110)
@@ -57,6 +68,9 @@ mod cuda {
         fn bb_merkle_open_batch_device(d_nodes: *const u8, nleaves: usize, indices: *const u64, nq: usize, paths_out: *mut u8,
                                        pos_out: *mut u8, depth_out: *mut usize) -> CudaError;
         fn bb_gather_device(d_src: *const c_void, elem_bytes: usize, indices: *const u64, nq: usize, out: *mut c_void) -> CudaError;
+        // every opening of a proof in one launch (24 trees, ~2100 leaves at 2^20 rows): requests cover indices[0..nq) in order
+        fn bb_merkle_open_multi_device(reqs: *const OpenRequest, nreq: usize, indices: *const u64, nq: usize, elem_bytes: usize,
+                                       paths_out: *mut u8, paths_bytes: usize, pos_out: *mut u8, vals_out: *mut u8, salts_out: *mut u8) -> CudaError;
         // the rest of what a device-resident StarkProver::generate_proof calls (toyni_b200/host/toyni_prover.hpp is that loop
         // in C++)
         fn bb_pool_alloc(d_ptr: *mut *mut c_void, bytes: usize) -> CudaError;
