@@ -494,7 +494,7 @@ def run_ours(args, rank, world, local_rank):
     # the library's stream-ordered API (bb_set_stream): one transform's tail (the last tiles of a pass leave SMs idle)
     # is filled by the other's kernels.  Buffer i % NB always goes to stream i % NS (NB is a multiple of NS), so no
     # buffer is ever touched from two streams.
-    NS = 2
+    NS = int(os.environ.get("TOYNI_BENCH_STREAMS", 2))  # 2 measured best (4: same within noise)
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
 
     def step(i):
